@@ -1,0 +1,135 @@
+// Shared internals of libfava_b200: context, error reporting, launch accounting, load helpers.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <map>
+#include <string>
+#include <tuple>
+
+#include "fava_b200.h"
+
+namespace fava {
+
+extern thread_local std::string g_last_error;
+extern std::atomic<int64_t> g_launches;
+
+int set_error(int code, const char* fmt, ...);
+
+#define FAVA_CHECK_CUDA(expr)                                                                  \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return fava::set_error(FAVA_ECUDA, "%s failed: %s (%s:%d)", #expr,                 \
+                                   cudaGetErrorString(e__), __FILE__, __LINE__);               \
+    } while (0)
+
+#define FAVA_CHECK_CUFFT(expr)                                                                 \
+    do {                                                                                       \
+        cufftResult r__ = (expr);                                                              \
+        if (r__ != CUFFT_SUCCESS)                                                              \
+            return fava::set_error(FAVA_ECUDA, "%s failed: cufftResult %d (%s:%d)", #expr,     \
+                                   (int)r__, __FILE__, __LINE__);                              \
+    } while (0)
+
+#define FAVA_REQUIRE(cond, ...)                                                                \
+    do {                                                                                       \
+        if (!(cond)) return fava::set_error(FAVA_EINVAL, __VA_ARGS__);                         \
+    } while (0)
+
+// Count and check a kernel launch.
+#define FAVA_LAUNCHED()                                                                        \
+    do {                                                                                       \
+        fava::g_launches.fetch_add(1, std::memory_order_relaxed);                              \
+        FAVA_CHECK_CUDA(cudaGetLastError());                                                   \
+    } while (0)
+
+constexpr int kNumSMsB200 = 148;
+
+enum WorkspaceSlot { WS_PARTIALS = 0, WS_TABLE = 1, WS_AUX = 2, WS_FFT0 = 3, WS_FFT1 = 4, WS_FFT2 = 5,
+                     WS_FFTIN = 6, WS_COUNT = 7 };
+
+struct Staging;  // pinned ring + reader threads (staging.cu)
+
+}  // namespace fava
+
+struct fava_ctx {
+    int device = 0;
+    int num_sms = fava::kNumSMsB200;
+    void* ws[fava::WS_COUNT] = {};
+    size_t ws_bytes[fava::WS_COUNT] = {};
+    // cuFFT plans keyed by (kind, a, b, c)
+    std::map<std::tuple<int, int64_t, int64_t, int64_t>, cufftHandle> plans;
+    fava::Staging* staging = nullptr;
+};
+
+namespace fava {
+
+// Grow-only device workspace owned by the context.
+int ctx_workspace(fava_ctx* ctx, int slot, size_t bytes, void** out);
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// ---- device helpers ---------------------------------------------------------------------------
+
+// Streaming (evict-first) vector loads widened to fp64 in registers.  f32 -> f64 widening is exact,
+// i.e. bit-identical to numpy's astype(float64) in the reference loader (_flash.py:333).
+template <typename T, int V>
+struct VecLoad;
+
+template <>
+struct VecLoad<double, 1> {
+    static __device__ __forceinline__ void ld(const double* p, double (&v)[1]) { v[0] = __ldcs(p); }
+};
+template <>
+struct VecLoad<double, 2> {
+    static __device__ __forceinline__ void ld(const double* p, double (&v)[2]) {
+        double2 t = __ldcs(reinterpret_cast<const double2*>(p));
+        v[0] = t.x;
+        v[1] = t.y;
+    }
+};
+template <>
+struct VecLoad<float, 1> {
+    static __device__ __forceinline__ void ld(const float* p, double (&v)[1]) { v[0] = (double)__ldcs(p); }
+};
+template <>
+struct VecLoad<float, 2> {
+    static __device__ __forceinline__ void ld(const float* p, double (&v)[2]) {
+        float2 t = __ldcs(reinterpret_cast<const float2*>(p));
+        v[0] = (double)t.x;
+        v[1] = (double)t.y;
+    }
+};
+template <>
+struct VecLoad<float, 4> {
+    static __device__ __forceinline__ void ld(const float* p, double (&v)[4]) {
+        float4 t = __ldcs(reinterpret_cast<const float4*>(p));
+        v[0] = (double)t.x;
+        v[1] = (double)t.y;
+        v[2] = (double)t.z;
+        v[3] = (double)t.w;
+    }
+};
+
+__device__ __forceinline__ double warp_sum_fixed(double v) {
+    // xor-butterfly: every lane ends with the same value, summation order fixed by lane ids
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace fava

@@ -1,0 +1,434 @@
+// K1/K2 — Reynolds / Favre plane statistics for sm_100a.
+//
+// Replaces the two hot loops of FLASH.reynolds_stress (reference fava/mesh/FLASH/_flash.py:1564-1577
+// plane means, :1584-1604 stresses).  One streaming pass reads rho,ux,uy,uz exactly once
+// (32 B/cell fp64, 16 B/cell f32) and produces 13 pivoted raw moments per plane
+//     S0 = sum rho, Sd_i = sum d_i, Srd_i = sum rho d_i, Srdd_ij = sum rho d_i d_j,  d_i = u_i - c_i
+// from which means, <rho u'_i u'_j> (Reynolds, volume-averaged means as in the reference) and the
+// Favre quantities follow algebraically.  The pivot c_i (first cell of the plane)
+// keeps the single pass within ~1e-14 of the reference's two-pass arithmetic.
+//
+// Determinism: level 1 = per-thread sequential accumulation + fixed-pattern warp/block reduction into
+// a per-CTA partial; level 2 = k_reduce_partials sums the partials of a bin in ascending chunk order.
+// No floating-point atomics anywhere.
+//
+// HBM-bound (19 DFMA-class ops per 32 B): the design goal is bytes in flight — 128-bit streaming
+// loads (ld.global.cs), U rows unrolled so each thread keeps 4*U independent 16 B requests
+// outstanding, two 256-thread CTAs per SM, grid of many equal work items (>= 16 waves) so the tail
+// wave is < 5 %.
+#include "common.cuh"
+
+namespace fava {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kNM = FAVA_NMOM - 1;  // 13 accumulated moments; row 13 (W) is analytic for dense input
+
+struct Acc {
+    double m[kNM];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int i = 0; i < kNM; ++i) m[i] = 0.0;
+    }
+    __device__ __forceinline__ void add(double r, double x, double y, double z, double c0, double c1,
+                                        double c2) {
+        const double dx = x - c0, dy = y - c1, dz = z - c2;
+        const double rx = r * dx, ry = r * dy, rz = r * dz;
+        m[0] += r;
+        m[1] += dx;
+        m[2] += dy;
+        m[3] += dz;
+        m[4] += rx;
+        m[5] += ry;
+        m[6] += rz;
+        m[7] = fma(rx, dx, m[7]);
+        m[8] = fma(rx, dy, m[8]);
+        m[9] = fma(rx, dz, m[9]);
+        m[10] = fma(ry, dy, m[10]);
+        m[11] = fma(ry, dz, m[11]);
+        m[12] = fma(rz, dz, m[12]);
+    }
+};
+
+// ---- axis 0 (x, the fastest index): column sums -----------------------------------------------
+// A warp owns a 32*V-column strip, a CTA's 8 warps take 8 consecutive rows per step; every thread
+// keeps 13*V accumulators for its V columns.  grid = (column strips, row chunks).
+template <typename T, int V, int U>
+__global__ void __launch_bounds__(kThreads, 2)
+    k_moments_cols(const T* __restrict__ rho, const T* __restrict__ ux, const T* __restrict__ uy,
+                   const T* __restrict__ uz, int64_t nrows, int64_t nx, const double* __restrict__ piv,
+                   double* __restrict__ partial, int64_t rows_per_chunk) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t x0 = ((int64_t)blockIdx.x * 32 + lane) * V;
+    const bool active = x0 < nx;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
+    const int64_t r1 = min(nrows, r0 + rows_per_chunk);
+
+    Acc acc[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v].clear();
+
+    if (active) {
+        double c[3][V];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int v = 0; v < V; ++v) c[i][v] = piv[i * nx + x0 + v];
+
+        int64_t r = r0 + warp;
+        for (; r + (int64_t)(U - 1) * kWarps < r1; r += (int64_t)U * kWarps) {
+            double vr[U][V], vx[U][V], vy[U][V], vz[U][V];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t off = (r + (int64_t)u * kWarps) * nx + x0;
+                VecLoad<T, V>::ld(rho + off, vr[u]);
+                VecLoad<T, V>::ld(ux + off, vx[u]);
+                VecLoad<T, V>::ld(uy + off, vy[u]);
+                VecLoad<T, V>::ld(uz + off, vz[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int v = 0; v < V; ++v)
+                    acc[v].add(vr[u][v], vx[u][v], vy[u][v], vz[u][v], c[0][v], c[1][v], c[2][v]);
+        }
+        for (; r < r1; r += kWarps) {
+            double vr[V], vx[V], vy[V], vz[V];
+            const int64_t off = r * nx + x0;
+            VecLoad<T, V>::ld(rho + off, vr);
+            VecLoad<T, V>::ld(ux + off, vx);
+            VecLoad<T, V>::ld(uy + off, vy);
+            VecLoad<T, V>::ld(uz + off, vz);
+#pragma unroll
+            for (int v = 0; v < V; ++v) acc[v].add(vr[v], vx[v], vy[v], vz[v], c[0][v], c[1][v], c[2][v]);
+        }
+    }
+
+    // fixed-order sum over the CTA's 8 warps, one moment at a time through 2 KB * V of smem
+    __shared__ double sm[kWarps][32 * V];
+    double* out = partial + (int64_t)blockIdx.y * kNM * nx;
+#pragma unroll
+    for (int m = 0; m < kNM; ++m) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) sm[warp][lane * V + v] = acc[v].m[m];
+        __syncthreads();
+        if (warp == 0 && active) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                double s = sm[0][lane * V + v];
+#pragma unroll
+                for (int w = 1; w < kWarps; ++w) s += sm[w][lane * V + v];
+                out[(int64_t)m * nx + x0 + v] = s;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- axis 1 / 2: every row of a bin goes to the same bin ---------------------------------------
+// A bin is `rows_per_bin` rows of `row_len` contiguous elements: row j of bin b starts at
+// b*bin_stride + j*row_stride (axis y: bin_stride=nx, row_stride=ny*nx; axis z: the plane is
+// contiguous).  grid = (bins, row chunks); a CTA streams whole rows (4 KB per step for fp64) with
+// 13 accumulators per thread, then block-reduces in a fixed pattern.
+template <typename T, int V, int U>
+__global__ void __launch_bounds__(kThreads, 2)
+    k_moments_rows(const T* __restrict__ rho, const T* __restrict__ ux, const T* __restrict__ uy,
+                   const T* __restrict__ uz, int64_t row_len, int64_t bin_stride, int64_t row_stride,
+                   int64_t rows_per_bin, int64_t rows_per_chunk, const double* __restrict__ piv,
+                   int64_t nbins, double* __restrict__ partial, int lanes_x) {
+    const int64_t bin = blockIdx.x;
+    const int tx = threadIdx.x % lanes_x, ty = threadIdx.x / lanes_x;
+    const int rpi = kThreads / lanes_x;
+    const int64_t j0 = (int64_t)blockIdx.y * rows_per_chunk;
+    const int64_t j1 = min(rows_per_bin, j0 + rows_per_chunk);
+    const double c0 = piv[bin], c1 = piv[nbins + bin], c2 = piv[2 * nbins + bin];
+    const int64_t base = bin * bin_stride;
+
+    Acc acc;
+    acc.clear();
+
+    for (int64_t xv = (int64_t)tx * V; xv < row_len; xv += (int64_t)lanes_x * V) {
+        int64_t j = j0 + ty;
+        for (; j + (int64_t)(U - 1) * rpi < j1; j += (int64_t)U * rpi) {
+            double vr[U][V], vx[U][V], vy[U][V], vz[U][V];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t off = base + (j + (int64_t)u * rpi) * row_stride + xv;
+                VecLoad<T, V>::ld(rho + off, vr[u]);
+                VecLoad<T, V>::ld(ux + off, vx[u]);
+                VecLoad<T, V>::ld(uy + off, vy[u]);
+                VecLoad<T, V>::ld(uz + off, vz[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int v = 0; v < V; ++v) acc.add(vr[u][v], vx[u][v], vy[u][v], vz[u][v], c0, c1, c2);
+        }
+        for (; j < j1; j += rpi) {
+            double vr[V], vx[V], vy[V], vz[V];
+            const int64_t off = base + j * row_stride + xv;
+            VecLoad<T, V>::ld(rho + off, vr);
+            VecLoad<T, V>::ld(ux + off, vx);
+            VecLoad<T, V>::ld(uy + off, vy);
+            VecLoad<T, V>::ld(uz + off, vz);
+#pragma unroll
+            for (int v = 0; v < V; ++v) acc.add(vr[v], vx[v], vy[v], vz[v], c0, c1, c2);
+        }
+    }
+
+    __shared__ double sm[kNM][kWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int m = 0; m < kNM; ++m) {
+        const double s = warp_sum_fixed(acc.m[m]);
+        if (lane == 0) sm[m][warp] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < kNM) {
+        double s = sm[threadIdx.x][0];
+#pragma unroll
+        for (int w = 1; w < kWarps; ++w) s += sm[threadIdx.x][w];
+        partial[((int64_t)blockIdx.y * kNM + threadIdx.x) * nbins + bin] = s;
+    }
+}
+
+// ---- level 2: partials -> moments --------------------------------------------------------------
+__global__ void k_reduce_partials(const double* __restrict__ partial, int nchunk, int64_t nbins,
+                                  double* __restrict__ mom, int accumulate, double cells_per_bin) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)FAVA_NMOM * nbins) return;
+    const int64_t m = idx / nbins, b = idx - m * nbins;
+    double s;
+    if (m < kNM) {
+        s = 0.0;
+        for (int c = 0; c < nchunk; ++c) s += partial[((int64_t)c * kNM + m) * nbins + b];
+    } else {
+        s = cells_per_bin;
+    }
+    mom[idx] = accumulate ? mom[idx] + s : s;
+}
+
+template <typename T>
+__global__ void k_plane_pivots(const T* __restrict__ ux, const T* __restrict__ uy, const T* __restrict__ uz,
+                               int64_t stride, int64_t nbins, double* __restrict__ piv) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbins) return;
+    piv[b] = (double)ux[b * stride];
+    piv[nbins + b] = (double)uy[b * stride];
+    piv[2 * nbins + b] = (double)uz[b * stride];
+}
+
+// Moments about c_old -> moments about c_new.  With e = c_old - c_new, d' = d + e:
+//   Sd' = Sd + n e,  Srd' = Srd + e S0,  Srdd'_ij = Srdd_ij + e_i Srd_j + e_j Srd_i + e_i e_j S0
+// where n = W (cell count, or weight sum for weighted moments).
+__global__ void k_repivot(double* __restrict__ mom, const double* __restrict__ pold,
+                          const double* __restrict__ pnew, int64_t nbins) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbins) return;
+    double e[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) e[i] = pold[i * nbins + b] - pnew[i * nbins + b];
+    const double s0 = mom[b], w = mom[13 * nbins + b];
+    double srd[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) srd[i] = mom[(4 + i) * nbins + b];
+    int k = 7;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = i; j < 3; ++j, ++k)
+            mom[k * nbins + b] += e[i] * srd[j] + e[j] * srd[i] + e[i] * e[j] * s0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        mom[(1 + i) * nbins + b] += w * e[i];
+        mom[(4 + i) * nbins + b] = srd[i] + e[i] * s0;
+    }
+}
+
+// Moments -> profiles.  With all sums scaled by `weight`:
+//   <q>      = sum(vf q)/LV                                          (_flash.py:1579-1582)
+//   m_i      = <u_i> - c_i = (Sd_i + c_i (W - LV)) / LV
+//   R_ij     = (Srdd_ij - m_i Srd_j - m_j Srd_i + m_i m_j S0) / LV   (_flash.py:1597-1609)
+//   u~_i     = c_i + Srd_i/S0 ;  F_ij = (Srdd_ij - Srd_i Srd_j / S0) / LV
+__global__ void k_finalize(const double* __restrict__ mom, const double* __restrict__ piv, int64_t nbins,
+                           double weight, double lv, double* __restrict__ means, double* __restrict__ rey,
+                           double* __restrict__ fmeans, double* __restrict__ favre) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbins) return;
+    const double s0 = mom[b] * weight;
+    const double w = mom[13 * nbins + b] * weight;
+    double c[3], sd[3], srd[3], m[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        c[i] = piv[i * nbins + b];
+        sd[i] = mom[(1 + i) * nbins + b] * weight;
+        srd[i] = mom[(4 + i) * nbins + b] * weight;
+        m[i] = (sd[i] + c[i] * (w - lv)) / lv;
+    }
+    if (means) {
+        means[b] = s0 / lv;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) means[(1 + i) * nbins + b] = c[i] + m[i];
+    }
+    if (fmeans) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) fmeans[i * nbins + b] = c[i] + srd[i] / s0;
+    }
+    int k = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = i; j < 3; ++j, ++k) {
+            const double srdd = mom[(7 + k) * nbins + b] * weight;
+            if (rey) rey[k * nbins + b] = (srdd - m[i] * srd[j] - m[j] * srd[i] + m[i] * m[j] * s0) / lv;
+            if (favre) favre[k * nbins + b] = (srdd - srd[i] * srd[j] / s0) / lv;
+        }
+}
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+
+static bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+template <typename T, int V, int U>
+static int launch_dense(fava_ctx* ctx, const T* rho, const T* ux, const T* uy, const T* uz, int64_t nz,
+                        int64_t ny, int64_t nx, int axis, const double* piv, double* mom, int accumulate,
+                        cudaStream_t st) {
+    const int64_t nbins = axis == 0 ? nx : (axis == 1 ? ny : nz);
+    const int64_t target_items = (int64_t)ctx->num_sms * 2 * 16;  // >= 16 waves of 2 CTAs/SM
+    double* partial = nullptr;
+    int nchunk = 1;
+    if (axis == 0) {
+        const int64_t nrows = nz * ny;
+        const int64_t strips = ceil_div(nx, 32 * V);
+        const int64_t step = (int64_t)kWarps * U;
+        int64_t want = std::max<int64_t>(1, target_items / strips);
+        int64_t rpc = round_up(ceil_div(nrows, want), step);
+        nchunk = (int)ceil_div(nrows, rpc);
+        void* ws;
+        int rc = ctx_workspace(ctx, WS_PARTIALS, sizeof(double) * (size_t)nchunk * kNM * nbins, &ws);
+        if (rc) return rc;
+        partial = (double*)ws;
+        dim3 grid((unsigned)strips, (unsigned)nchunk);
+        k_moments_cols<T, V, U><<<grid, kThreads, 0, st>>>(rho, ux, uy, uz, nrows, nx, piv, partial, rpc);
+        FAVA_LAUNCHED();
+    } else {
+        int64_t row_len, bin_stride, row_stride, rows_per_bin;
+        if (axis == 1) {
+            row_len = nx, bin_stride = nx, row_stride = ny * nx, rows_per_bin = nz;
+        } else {
+            // the plane is contiguous: re-tile it into rows of one CTA-wide vector step
+            const int64_t plane = ny * nx, tile = (int64_t)kThreads * V;
+            bin_stride = plane;
+            if (plane % tile == 0) row_len = tile, rows_per_bin = plane / tile;
+            else row_len = nx, rows_per_bin = ny;
+            row_stride = row_len;
+        }
+        int lanes_x = kThreads;
+        while (lanes_x > 1 && (int64_t)(lanes_x / 2) * V >= row_len) lanes_x /= 2;
+        const int rpi = kThreads / lanes_x;
+        const int64_t step = (int64_t)rpi * U;
+        int64_t want = std::max<int64_t>(1, ceil_div(target_items, nbins));
+        int64_t rpc = round_up(ceil_div(rows_per_bin, want), step);
+        nchunk = (int)ceil_div(rows_per_bin, rpc);
+        void* ws;
+        int rc = ctx_workspace(ctx, WS_PARTIALS, sizeof(double) * (size_t)nchunk * kNM * nbins, &ws);
+        if (rc) return rc;
+        partial = (double*)ws;
+        dim3 grid((unsigned)nbins, (unsigned)nchunk);
+        k_moments_rows<T, V, U><<<grid, kThreads, 0, st>>>(rho, ux, uy, uz, row_len, bin_stride, row_stride,
+                                                          rows_per_bin, rpc, piv, nbins, partial, lanes_x);
+        FAVA_LAUNCHED();
+    }
+    const int64_t n = (int64_t)FAVA_NMOM * nbins;
+    const double cells = (double)(nz * ny * nx / nbins);
+    k_reduce_partials<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(partial, nchunk, nbins, mom, accumulate, cells);
+    FAVA_LAUNCHED();
+    return FAVA_OK;
+}
+
+template <typename T, int U>
+static int dispatch_dense(fava_ctx* ctx, const void* rho, const void* ux, const void* uy, const void* uz,
+                          int64_t nz, int64_t ny, int64_t nx, int axis, const double* piv, double* mom,
+                          int accumulate, cudaStream_t st) {
+    const size_t va = 2 * sizeof(T);
+    const bool vec = (nx % 2 == 0) && aligned_to(rho, va) && aligned_to(ux, va) && aligned_to(uy, va) &&
+                     aligned_to(uz, va);
+    if (vec)
+        return launch_dense<T, 2, U>(ctx, (const T*)rho, (const T*)ux, (const T*)uy, (const T*)uz, nz, ny, nx,
+                                     axis, piv, mom, accumulate, st);
+    return launch_dense<T, 1, U>(ctx, (const T*)rho, (const T*)ux, (const T*)uy, (const T*)uz, nz, ny, nx, axis,
+                                 piv, mom, accumulate, st);
+}
+
+}  // namespace fava
+
+using namespace fava;
+
+extern "C" {
+
+int fava_plane_pivots(fava_ctx* ctx, const void* d_ux, const void* d_uy, const void* d_uz, int dtype,
+                      int64_t nz, int64_t ny, int64_t nx, int axis, double* d_pivots, void* stream) {
+    FAVA_REQUIRE(ctx && d_ux && d_uy && d_uz && d_pivots, "fava_plane_pivots: NULL argument");
+    FAVA_REQUIRE(nz > 0 && ny > 0 && nx > 0, "fava_plane_pivots: empty array %lldx%lldx%lld", (long long)nz,
+                 (long long)ny, (long long)nx);
+    FAVA_REQUIRE(axis >= 0 && axis <= 2, "fava_plane_pivots: axis %d not in 0..2", axis);
+    FAVA_REQUIRE(dtype == FAVA_F32 || dtype == FAVA_F64, "fava_plane_pivots: bad dtype %d", dtype);
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t nbins = axis == 0 ? nx : (axis == 1 ? ny : nz);
+    const int64_t stride = axis == 0 ? 1 : (axis == 1 ? nx : ny * nx);
+    const unsigned grid = (unsigned)ceil_div(nbins, 256);
+    if (dtype == FAVA_F64)
+        k_plane_pivots<double><<<grid, 256, 0, st>>>((const double*)d_ux, (const double*)d_uy,
+                                                     (const double*)d_uz, stride, nbins, d_pivots);
+    else
+        k_plane_pivots<float><<<grid, 256, 0, st>>>((const float*)d_ux, (const float*)d_uy, (const float*)d_uz,
+                                                    stride, nbins, d_pivots);
+    FAVA_LAUNCHED();
+    return FAVA_OK;
+}
+
+int fava_plane_moments(fava_ctx* ctx, const void* d_rho, const void* d_ux, const void* d_uy,
+                       const void* d_uz, int dtype, int64_t nz, int64_t ny, int64_t nx, int axis,
+                       const double* d_pivots, double* d_moments, int accumulate, void* stream) {
+    FAVA_REQUIRE(ctx && d_rho && d_ux && d_uy && d_uz && d_pivots && d_moments,
+                 "fava_plane_moments: NULL argument");
+    FAVA_REQUIRE(nz > 0 && ny > 0 && nx > 0, "fava_plane_moments: empty array %lldx%lldx%lld", (long long)nz,
+                 (long long)ny, (long long)nx);
+    FAVA_REQUIRE(axis >= 0 && axis <= 2, "fava_plane_moments: axis %d not in 0..2", axis);
+    FAVA_REQUIRE(dtype == FAVA_F32 || dtype == FAVA_F64, "fava_plane_moments: bad dtype %d", dtype);
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == FAVA_F64)
+        return dispatch_dense<double, 4>(ctx, d_rho, d_ux, d_uy, d_uz, nz, ny, nx, axis, d_pivots, d_moments,
+                                         accumulate, st);
+    return dispatch_dense<float, 8>(ctx, d_rho, d_ux, d_uy, d_uz, nz, ny, nx, axis, d_pivots, d_moments,
+                                    accumulate, st);
+}
+
+int fava_moments_repivot(fava_ctx* ctx, double* d_moments, const double* d_piv_old, const double* d_piv_new,
+                         int64_t nbins, void* stream) {
+    FAVA_REQUIRE(ctx && d_moments && d_piv_old && d_piv_new, "fava_moments_repivot: NULL argument");
+    FAVA_REQUIRE(nbins > 0, "fava_moments_repivot: nbins must be positive");
+    DeviceGuard g(ctx->device);
+    k_repivot<<<(unsigned)ceil_div(nbins, 128), 128, 0, (cudaStream_t)stream>>>(d_moments, d_piv_old, d_piv_new,
+                                                                                nbins);
+    FAVA_LAUNCHED();
+    return FAVA_OK;
+}
+
+int fava_moments_finalize(fava_ctx* ctx, const double* d_moments, const double* d_pivots, int64_t nbins,
+                          double weight, double layer_volume, double* d_means, double* d_rey,
+                          double* d_fmeans, double* d_favre, void* stream) {
+    FAVA_REQUIRE(ctx && d_moments && d_pivots, "fava_moments_finalize: NULL argument");
+    FAVA_REQUIRE(nbins > 0, "fava_moments_finalize: nbins must be positive");
+    FAVA_REQUIRE(layer_volume > 0.0, "fava_moments_finalize: layer_volume must be positive");
+    DeviceGuard g(ctx->device);
+    k_finalize<<<(unsigned)ceil_div(nbins, 128), 128, 0, (cudaStream_t)stream>>>(
+        d_moments, d_pivots, nbins, weight, layer_volume, d_means, d_rey, d_fmeans, d_favre);
+    FAVA_LAUNCHED();
+    return FAVA_OK;
+}
+
+}  // extern "C"

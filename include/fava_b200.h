@@ -1,0 +1,203 @@
+/*
+ * fava_b200.h — C ABI of libfava_b200.so, the B200 (sm_100a) implementation of FAVA's
+ * grid-statistics hot path.
+ *
+ * The reference (ebrooker/FAVA) is pure Python and has no FFI of its own; the boundary a
+ * maintainer would bind is therefore the set of NumPy loops this library replaces.  Each entry
+ * point below cites the reference code it stands in for (paths relative to the reference root).
+ * INTEGRATION.md shows the ctypes stub that binds them from the reference's mesh classes.
+ *
+ * Conventions
+ *   - plain C types only: pointers, sizes, ints, doubles.  No torch / C++ types cross the ABI.
+ *   - every pointer named d_* is a DEVICE pointer owned by the caller; h_* is a HOST pointer.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls enqueue
+ *     work on that stream and return; results are valid after the stream is synchronised
+ *     (fava_stream_sync or the caller's own event).
+ *   - all functions return FAVA_OK (0) or a negative FAVA_E* code and never throw; the message
+ *     for the calling thread's last failure is fava_last_error().
+ *   - field arrays use the FLASH *file* layout: [z][y][x] (x fastest) for a uniform dataset,
+ *     [block][z][y][x] for a block dataset.  The reference's in-memory layout [x][y][z]
+ *     (fava/mesh/FLASH/_flash.py:314-335, a strided transpose on load) is never materialised.
+ *   - dtype: FAVA_F32 (plt files) or FAVA_F64 (chk files); f32 is widened to f64 in registers,
+ *     bit-identical to `.astype(np.float64)` (_flash.py:333).  All arithmetic is fp64.
+ *   - reductions are deterministic: fixed-order two-level accumulation, no floating-point atomics.
+ */
+#ifndef FAVA_B200_H
+#define FAVA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FAVA_ABI_VERSION 1
+
+/* status codes */
+#define FAVA_OK 0
+#define FAVA_EINVAL (-1)  /* bad argument (shape, dtype, axis, null pointer) */
+#define FAVA_ECUDA (-2)   /* CUDA runtime / cuFFT error; see fava_last_error() */
+#define FAVA_ENOMEM (-3)  /* workspace allocation failed */
+#define FAVA_EIO (-4)     /* staging: open/pread failed or short read */
+#define FAVA_ENODEV (-5)  /* no usable sm_100 device */
+
+/* storage dtypes of field arrays */
+#define FAVA_F32 0
+#define FAVA_F64 1
+
+/* number of moment rows produced per bin by the plane-moment kernels */
+#define FAVA_NMOM 14
+/*
+ * Moment rows (all vf-weighted where a weight applies), with d_i = u_i - c_i (c = pivot):
+ *   0        S0      = sum rho
+ *   1..3     Sd_i    = sum d_i                  (i = x,y,z)
+ *   4..6     Srd_i   = sum rho d_i
+ *   7..12    Srdd_ij = sum rho d_i d_j          (xx,xy,xz,yy,yz,zz)
+ *   13       W       = sum of weights (cells x vol_frac)
+ */
+
+typedef struct fava_ctx fava_ctx;
+
+/* ---- context ------------------------------------------------------------------------------- */
+
+/* Create a context bound to CUDA device `device` (the library owns workspaces, cuFFT plans and
+ * the pinned staging ring inside it).  Replaces the reference's FAVA_MPI singleton +
+ * shared-memory windows (fava/util/_mpi.py:7-80). */
+int fava_init(int device, fava_ctx** out);
+int fava_shutdown(fava_ctx* ctx);
+int fava_stream_sync(fava_ctx* ctx, void* stream);
+const char* fava_last_error(void);
+int fava_abi_version(void);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+int64_t fava_launch_count(void);
+
+/* ---- Reynolds / Favre plane statistics (reference: FLASH.reynolds_stress, _flash.py:1506-1611) */
+
+/* Per-bin pivots c_i[n] = u_i at the first cell of plane n (dense array).  d_pivots: [3][nbins]. */
+int fava_plane_pivots(fava_ctx* ctx, const void* d_ux, const void* d_uy, const void* d_uz, int dtype,
+                      int64_t nz, int64_t ny, int64_t nx, int axis, double* d_pivots, void* stream);
+
+/* One streaming pass over rho,ux,uy,uz [nz][ny][nx]: the FAVA_NMOM pivoted plane moments for
+ * every plane normal to `axis` (0 = x, the fastest index; 1 = y; 2 = z), unweighted.
+ * Replaces both hot loops of the reference (_flash.py:1564-1577 and :1584-1604).
+ * d_moments: [FAVA_NMOM][nbins], nbins = (nx,ny,nz)[axis].  If `accumulate` != 0 the result is
+ * added to d_moments (chunk-streamed slabs; axis-2 callers pass bin_offset instead).
+ * Row 13 (W) receives the cell count of each plane. */
+int fava_plane_moments(fava_ctx* ctx, const void* d_rho, const void* d_ux, const void* d_uy,
+                       const void* d_uz, int dtype, int64_t nz, int64_t ny, int64_t nx, int axis,
+                       const double* d_pivots, double* d_moments, int accumulate, void* stream);
+
+/* Block-list front end for FLASH block datasets [nblocks][nzb][nyb][nxb] (AMR or multi-block
+ * uniform plt files).  For leaf l of the table: planes i=0..nrb-1 of block blk[l] normal to `axis`
+ * contribute weight vf[l] to fine bins [ilo[l]+i*scale[l], ilo[l]+(i+1)*scale[l])
+ * (_flash.py:1559-1577, :1594-1604).  The table is built on the host exactly as the reference
+ * does (get_blocklist :803-822, vol_fracs :1559-1562, ilo :1566-1567, lref_n :1565).
+ * Outputs d_moments [FAVA_NMOM][nbins] and d_pivots [3][nbins] (pivot chosen per bin by the
+ * library: first cell of the first contributing block plane). */
+typedef struct fava_leaf_desc {
+    int64_t block;   /* index of the source block in the dataset */
+    int64_t ilo;     /* first fine bin covered by plane 0 */
+    int32_t scale;   /* lref_n = 2^(lmax - level): fine bins per block plane */
+    int32_t pad_;
+    double vol_frac; /* vf_b */
+} fava_leaf_desc;
+
+int fava_plane_moments_blocks(fava_ctx* ctx, const void* d_rho, const void* d_ux, const void* d_uy,
+                              const void* d_uz, int dtype, int64_t nzb, int64_t nyb, int64_t nxb,
+                              int axis, const fava_leaf_desc* h_leaves, int64_t nleaf, int64_t nbins,
+                              double* d_moments, double* d_pivots, void* stream);
+
+/* Re-express moments taken about pivots c_old about c_new (exact algebra; used before summing
+ * partial moments from different ranks / slabs whose pivots differ). In place on d_moments. */
+int fava_moments_repivot(fava_ctx* ctx, double* d_moments, const double* d_piv_old,
+                         const double* d_piv_new, int64_t nbins, void* stream);
+
+/* Moments -> profiles.  weight = vol_frac applied to unweighted (dense) moments, 1.0 for the
+ * block-list front end (already weighted); layer_volume as _flash.py:1526-1542.
+ *   d_means  [4][nbins]: dens, velx, vely, velz volume means            (_flash.py:1579-1582)
+ *   d_rey    [6][nbins]: <rho u'_i u'_j>  xx,xy,xz,yy,yz,zz              (_flash.py:1597-1609)
+ *   d_fmeans [3][nbins]: Favre means  u~_i = <rho u_i>/<rho>             (extension)
+ *   d_favre  [6][nbins]: <rho u''_i u''_j>                               (extension)
+ * Any output pointer may be NULL. */
+int fava_moments_finalize(fava_ctx* ctx, const double* d_moments, const double* d_pivots,
+                          int64_t nbins, double weight, double layer_volume, double* d_means,
+                          double* d_rey, double* d_fmeans, double* d_favre, void* stream);
+
+/* Single-moment variant: vf-weighted plane integral of one field (reference: slice_integral,
+ * _flash.py:1451-1504).  Dense array; d_out [nbins] = sum over plane (unweighted). */
+int fava_plane_sum(fava_ctx* ctx, const void* d_field, int dtype, int64_t nz, int64_t ny, int64_t nx,
+                   int axis, double* d_out, void* stream);
+
+/* ---- AMR -> uniform prolongation (reference: FLASH.from_amr gather, _flash.py:1262-1321) ----- */
+
+typedef struct fava_prolong_leaf {
+    int64_t block;    /* source block index */
+    int32_t off[3];   /* fine-cell corner of the block minus subdomain corner: x,y,z (may be <0) */
+    int32_t scale;    /* 2^(L - level) */
+} fava_prolong_leaf;
+
+/* Piecewise-constant injection of the selected leaves into a uniform [NZ][NY][NX] fp64 array.
+ * Later table entries win where leaves overlap (the reference's dict overwrite order,
+ * _flash.py:1305); cells no leaf covers are 0.0 (_flash.py:1258). */
+int fava_prolong(fava_ctx* ctx, const void* d_blocks, int dtype, int64_t nzb, int64_t nyb,
+                 int64_t nxb, const fava_prolong_leaf* h_leaves, int64_t nleaf, int64_t NZ,
+                 int64_t NY, int64_t NX, double* d_out, void* stream);
+
+/* ---- kinetic-energy spectrum (reference: FlashUniform.kinetic_energy_spectra,
+ *      fava/mesh/FLASH/FlashUniform.py:229-304) -------------------------------------------------- */
+
+/* Whole pipeline on one GPU for a cubic N^3 grid: w_n = sqrt(rho) u_n, 3-D FFT (cuFFT D2Z — the
+ * one library call on this path), |u^|^2 / longitudinal projection / shell binning, shell means
+ * x 4 pi k^2.  Outputs are HOST arrays of nbins = N/2 - 1 doubles (keys k,total,longitudinal,
+ * transverse of the reference's dict). */
+int fava_ke_spectrum(fava_ctx* ctx, const void* d_rho, const void* d_ux, const void* d_uy,
+                     const void* d_uz, int dtype, int64_t n, double* h_k, double* h_total,
+                     double* h_long, double* h_trans, void* stream);
+
+/* Building blocks of the same pipeline, exposed for the slab-decomposed (multi-GPU) driver. */
+
+/* w[n] = sqrt(rho) * u for one slab of nz_local planes; d_w real fp64 [nz_local][ny][nx]. */
+int fava_ke_weight(fava_ctx* ctx, const void* d_rho, const void* d_u, int dtype, int64_t ncells,
+                   double* d_w, void* stream);
+/* Batched FFTs of a slab: r2c along x then c2c along y for nz_local planes.
+ * in: real [nz_local][ny][nx]; out: complex [nz_local][ny][nx/2+1] (interleaved re,im). */
+int fava_fft_xy(fava_ctx* ctx, const double* d_in, double* d_out, int64_t nz_local, int64_t ny,
+                int64_t nx, void* stream);
+/* In-place c2c FFTs along the slowest axis of complex [nz][rows] (rows = ny_local*(nx/2+1)). */
+int fava_fft_z(fava_ctx* ctx, double* d_data, int64_t nz, int64_t rows, void* stream);
+/* Slab -> pencil pack for the all-to-all: splits complex [nz_local][ny][nxh] by destination rank
+ * along y into `nranks` contiguous send blocks [rank][nz_local][ny/nranks][nxh].  If d_peer_recv
+ * is non-NULL it holds `nranks` device pointers (peer-mapped receive buffers) and block r is
+ * written straight to d_peer_recv[r] + my_rank*block_elems (the exchange fused into the pack). */
+int fava_a2a_pack(fava_ctx* ctx, const double* d_in, double* d_send, double* const* d_peer_recv,
+                  int my_rank, int nranks, int64_t nz_local, int64_t ny, int64_t nxh, void* stream);
+/* Shell binning of one spectral sub-volume complex [nz][ny_local][nxh] x 3 components, holding
+ * ky indices [ky0, ky0+ny_local) of an N^3 transform normalised by `norm` (1/N^3).
+ * d_sums: [3][nbins] (total, longitudinal, count) partial sums, overwritten. */
+int fava_spectrum_bin(fava_ctx* ctx, const double* d_fx, const double* d_fy, const double* d_fz,
+                      int64_t n, int64_t ky0, int64_t ny_local, double norm, double* d_sums,
+                      void* stream);
+/* Shell sums -> spectra (host outputs, nbins = n/2-1 each). */
+int fava_spectrum_finalize(fava_ctx* ctx, const double* d_sums, int64_t n, double* h_k,
+                           double* h_total, double* h_long, double* h_trans, void* stream);
+
+/* ---- HDF5 block staging (reference: _read_variable_data, _flash.py:306-341) ----------------- */
+
+/* Stream `nbytes` at `file_offset` of a contiguous HDF5 dataset (offset from the h5lite index)
+ * into device memory through the context's pinned ring: pread by reader threads, one
+ * cudaMemcpyAsync per chunk on `stream`.  Returns after the last copy is enqueued. */
+int fava_stage_h2d(fava_ctx* ctx, const char* path, int64_t file_offset, int64_t nbytes,
+                   void* d_dst, void* stream);
+/* Same path for a caller-owned host buffer (pageable or pinned). */
+int fava_stage_host_h2d(fava_ctx* ctx, const void* h_src, int64_t nbytes, void* d_dst,
+                        void* stream);
+
+/* ---- CUDA IPC helpers for peer-mapped exchange buffers (one process per GPU) ---------------- */
+int fava_ipc_export(void* d_ptr, unsigned char handle_out[64]);
+int fava_ipc_open(const unsigned char handle[64], void** d_ptr_out);
+int fava_ipc_close(void* d_ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FAVA_B200_H */

@@ -1,0 +1,174 @@
+"""GPU parity: dense plane-moment kernels (through the C ABI) vs the NumPy oracle.
+
+Tolerance (BASELINE.json north_star): fp64 profiles within 1e-12 relative, max-norm per output array:
+max|a-b| <= 1e-12 * max|b|.
+"""
+
+import numpy as np
+import pytest
+
+from fava_b200 import synth
+from oracle import fava_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+
+
+def maxnorm_close(a, b, rtol=RTOL, what=""):
+    a = np.asarray(a)
+    b = np.asarray(b)
+    scale = np.max(np.abs(b))
+    err = np.max(np.abs(a - b))
+    assert err <= rtol * scale + 1e-300, f"{what}: max|a-b|={err:.3e} > {rtol:g}*max|b|={scale:.3e}"
+
+
+def run_gpu(fields, axis, cell_volume, layer_volume, dev):
+    import torch
+
+    from fava_b200 import device
+
+    t = {k: torch.from_numpy(v).to(dev) for k, v in fields.items()}
+    out = device.plane_profiles(t["dens"], t["velx"], t["vely"], t["velz"], axis, cell_volume, layer_volume)
+    return {k: v.cpu().numpy() for k, v in out.items()}
+
+
+def oracle_profiles(fields, axis, bounds):
+    nz, ny, nx = fields["dens"].shape
+    geom = orc.uniform_geom((nx, ny, nz), bounds, bbox_dtype=np.float64)
+    data = {k: orc.load_like_reference(v)[None, ...] for k, v in fields.items()}
+    radius, stress, means = orc.reynolds_stress(geom, data, axis=axis)
+    fmeans, favre = orc.favre_stress(geom, data, axis=axis)
+    return geom, radius, stress, means, fmeans, favre
+
+
+def compare(fields, axis, bounds, dev):
+    from fava_b200.device import MEAN_KEYS, STRESS_KEYS
+
+    geom, radius, stress, means, fmeans, favre = oracle_profiles(fields, axis, bounds)
+    cell_volume = geom.cell_volume_from_level(1)
+    db = geom.domain_bounds
+    others = [a for a in range(3) if a != axis]
+    layer_volume = (db[others[0], 1] - db[others[0], 0]) * (db[others[1], 1] - db[others[1], 0]) * geom.min_delta(axis)
+    got = run_gpu(fields, axis, cell_volume, layer_volume, dev)
+    for i, k in enumerate(MEAN_KEYS):
+        maxnorm_close(got["means"][i], means[k], what=f"mean {k} axis {axis}")
+    for i, k in enumerate(STRESS_KEYS):
+        maxnorm_close(got["reynolds"][i], stress[k], what=f"reynolds {k} axis {axis}")
+        maxnorm_close(got["favre"][i], favre[k], what=f"favre {k} axis {axis}")
+    for i, k in enumerate(("velx", "vely", "velz")):
+        maxnorm_close(got["favre_means"][i], fmeans[k], what=f"favre mean {k} axis {axis}")
+
+
+@pytest.mark.parametrize("axis", [0, 1, 2])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("shape", [(64, 64, 64), (32, 48, 80), (8, 8, 8)])
+def test_dense_profiles_vs_oracle(cuda_device, axis, dtype, shape):
+    fields = synth.uniform_fields(shape, names=("dens", "velx", "vely", "velz"), dtype=dtype, seed=1234)
+    compare(fields, axis, ((0.0, 1.0), (0.0, 1.0), (0.0, 1.0)), cuda_device)
+
+
+@pytest.mark.parametrize("axis", [0, 1, 2])
+def test_dense_profiles_large_mean_and_noncubic_extent(cuda_device, axis):
+    """mean/rms = 40 exercises the pivot; non-unit extents exercise cell/layer volumes."""
+    fields = synth.uniform_fields((48, 40, 56), names=("dens", "velx", "vely", "velz"), u0=10.0, seed=77)
+    compare(fields, axis, ((0.0, 2.0), (0.0, 1.0), (-1.0, 1.0)), cuda_device)
+
+
+@pytest.mark.parametrize("axis", [0, 1, 2])
+def test_odd_sizes_take_scalar_path(cuda_device, axis):
+    fields = synth.uniform_fields((7, 9, 11), names=("dens", "velx", "vely", "velz"), seed=5)
+    compare(fields, axis, ((0.0, 1.0), (0.0, 1.0), (0.0, 1.0)), cuda_device)
+
+
+@pytest.mark.parametrize("axis", [0, 1, 2])
+def test_constant_velocity_gives_zero_stress(cuda_device, axis):
+    """constant velocity => R_ij = 0 (exactly, thanks to the pivot)."""
+    import torch
+
+    from fava_b200 import device
+
+    shape = (32, 32, 32)
+    rho = torch.from_numpy(synth.field_slab("dens", shape)).to(cuda_device)
+    u = [torch.full(shape, v, dtype=torch.float64, device=cuda_device) for v in (3.0, -2.0, 0.5)]
+    out = device.plane_profiles(rho, u[0], u[1], u[2], axis, 1.0 / 32**3, 1.0 / 32)
+    assert float(out["reynolds"].abs().max()) == 0.0
+    assert float(out["favre"].abs().max()) == 0.0
+
+
+def test_constant_density_favre_equals_reynolds(cuda_device):
+    import torch
+
+    from fava_b200 import device
+
+    shape = (32, 32, 32)
+    f = synth.uniform_fields(shape, names=("velx", "vely", "velz"))
+    rho = torch.full(shape, 2.0, dtype=torch.float64, device=cuda_device)
+    u = [torch.from_numpy(f[k]).to(cuda_device) for k in ("velx", "vely", "velz")]
+    out = device.plane_profiles(rho, u[0], u[1], u[2], 0, 1.0 / 32**3, 1.0 / 32)
+    r, fv = out["reynolds"].cpu().numpy(), out["favre"].cpu().numpy()
+    maxnorm_close(fv, r, rtol=1e-13, what="favre vs reynolds at constant density")
+
+
+def test_run_to_run_bitwise_determinism(cuda_device):
+    import torch
+
+    from fava_b200 import device
+
+    shape = (64, 64, 64)
+    f = synth.uniform_fields(shape, names=("dens", "velx", "vely", "velz"))
+    t = [torch.from_numpy(f[k]).to(cuda_device) for k in ("dens", "velx", "vely", "velz")]
+    for axis in (0, 1, 2):
+        a, _ = device.plane_moments(*t, axis)
+        b, _ = device.plane_moments(*t, axis)
+        assert torch.equal(a, b)
+
+
+def test_accumulate_over_z_slabs_matches_one_shot(cuda_device):
+    """Chunk-streamed slabs (config 5): moments accumulated slab by slab == whole array (axes x, y)."""
+    import torch
+
+    from fava_b200 import device
+
+    shape = (48, 32, 64)
+    f = synth.uniform_fields(shape, names=("dens", "velx", "vely", "velz"))
+    t = [torch.from_numpy(f[k]).to(cuda_device) for k in ("dens", "velx", "vely", "velz")]
+    for axis in (0, 1):
+        whole, piv = device.plane_moments(*t, axis)
+        acc = torch.zeros_like(whole)
+        for z0 in range(0, 48, 16):
+            sl = [x[z0 : z0 + 16].contiguous() for x in t]
+            device.plane_moments(*sl, axis, pivots=piv, out=acc, accumulate=True)
+        w = whole.cpu().numpy()
+        maxnorm_close(acc.cpu().numpy(), w, rtol=1e-13, what=f"slab accumulate axis {axis}")
+
+
+def test_repivot_is_consistent(cuda_device):
+    import torch
+
+    from fava_b200 import device
+
+    shape = (32, 32, 32)
+    f = synth.uniform_fields(shape, names=("dens", "velx", "vely", "velz"), u0=1.0)
+    t = [torch.from_numpy(f[k]).to(cuda_device) for k in ("dens", "velx", "vely", "velz")]
+    mom, piv = device.plane_moments(*t, 0)
+    piv2 = piv + 0.125
+    mom2, _ = device.plane_moments(*t, 0, pivots=piv2)
+    device.moments_repivot(mom, piv, piv2)
+    maxnorm_close(mom.cpu().numpy(), mom2.cpu().numpy(), rtol=1e-13, what="repivot")
+
+
+def test_bad_arguments_raise(cuda_device):
+    import torch
+
+    from fava_b200 import device
+
+    x = torch.zeros((4, 4, 4), dtype=torch.float64, device=cuda_device)
+    with pytest.raises(ValueError):
+        device.plane_moments(x, x, x, x, 3)
+    with pytest.raises(TypeError):
+        h = x.to(torch.float16)
+        device.plane_moments(h, h, h, h, 0)
+    with pytest.raises(ValueError):
+        c = x.cpu()
+        device.plane_moments(c, c, c, c, 0)
