@@ -72,6 +72,10 @@ SIGNATURES: dict[str, tuple] = {
         [c_void_p, c_void_p, c_void_p, c_i64, c_double, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     ),
     "fava_plane_sum": (c_int, [c_void_p, c_void_p, c_int, c_i64, c_i64, c_i64, c_int, c_void_p, c_void_p]),
+    "fava_plane_sum_blocks": (
+        c_int,
+        [c_void_p, c_void_p, c_int, c_i64, c_i64, c_i64, c_int, C.POINTER(LeafDesc), c_i64, c_i64, c_void_p, c_void_p],
+    ),
     "fava_prolong": (
         c_int,
         [c_void_p, c_void_p, c_int, c_i64, c_i64, c_i64, C.POINTER(ProlongLeaf), c_i64, c_i64, c_i64, c_i64,
@@ -82,8 +86,12 @@ SIGNATURES: dict[str, tuple] = {
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_double_p, c_double_p, c_double_p,
          c_double_p, c_void_p],
     ),
-    "fava_ke_weight": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_i64, c_void_p, c_void_p]),
-    "fava_fft_xy": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p]),
+    "fava_ke_weight3": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_i64, c_i64, c_void_p, c_void_p, c_void_p,
+         c_void_p],
+    ),
+    "fava_fft_xy": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p]),
     "fava_fft_z": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_void_p]),
     "fava_a2a_pack": (
         c_int,
@@ -91,7 +99,7 @@ SIGNATURES: dict[str, tuple] = {
     ),
     "fava_spectrum_bin": (
         c_int,
-        [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_double, c_void_p, c_void_p],
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_void_p, c_double, c_void_p, c_void_p],
     ),
     "fava_spectrum_finalize": (
         c_int,

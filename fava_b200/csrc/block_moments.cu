@@ -1,0 +1,456 @@
+// K1 block-list front end — Reynolds / Favre plane moments of FLASH block datasets
+// [nblocks][nzb][nyb][nxb] (AMR plt/chk files and multi-block uniform files).
+//
+// Replaces the per-leaf-block NumPy loops of FLASH.reynolds_stress (reference
+// fava/mesh/FLASH/_flash.py:1564-1577 pass 1, :1584-1604 pass 2; ~1 ms of Python per block).
+//
+// Stage 1 (k_block_moments_*): one pass over the leaf blocks; every (leaf, block-plane) "item"
+//   gets its 13 pivoted raw moments (same set as plane_moments.cu), taken about the pivot of the
+//   FIRST fine bin the plane covers.  Each leaf's cells are read exactly once: 4*s bytes per cell.
+// Stage 2 (k_combine_items): one CTA per fine bin walks the bin's item list (CSR built on the host
+//   from the leaf table, leaf order preserved), re-expresses each item's moments about the bin's own
+//   pivot (exact algebra, a no-op on single-level meshes), weights by vol_frac and sums in a fixed
+//   order.  A coarse block plane (scale = 2^(lmax-level) > 1) feeds `scale` fine bins, exactly like
+//   the reference's means[jlo:jhi] += ... / `for ii in range(mapping...)` (_flash.py:1576, :1596).
+// No floating-point atomics: results are bitwise reproducible.
+#include <vector>
+
+#include "common.cuh"
+
+namespace fava {
+
+constexpr int kBT = 256;  // threads per CTA in stage 1
+constexpr int kNMb = 13;
+
+struct Acc13 {
+    double m[kNMb];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int i = 0; i < kNMb; ++i) m[i] = 0.0;
+    }
+    __device__ __forceinline__ void add(double r, double x, double y, double z, double c0, double c1, double c2) {
+        const double dx = x - c0, dy = y - c1, dz = z - c2;
+        const double rx = r * dx, ry = r * dy, rz = r * dz;
+        m[0] += r;
+        m[1] += dx;
+        m[2] += dy;
+        m[3] += dz;
+        m[4] += rx;
+        m[5] += ry;
+        m[6] += rz;
+        m[7] = fma(rx, dx, m[7]);
+        m[8] = fma(rx, dy, m[8]);
+        m[9] = fma(rx, dz, m[9]);
+        m[10] = fma(ry, dy, m[10]);
+        m[11] = fma(ry, dz, m[11]);
+        m[12] = fma(rz, dz, m[12]);
+    }
+};
+
+// ---- stage 1, fast path: power-of-two blocks with nxb*nyb <= 256 <= cells --------------------------
+// One CTA per leaf.  Every thread owns ONE plane for the whole block (so it accumulates in registers)
+// and walks the block with fully coalesced loads:
+//   axis x: element e = t + 256 r          -> x = t mod nxb                     (plane = t & (nxb-1))
+//   axis y: same walk                      -> y = (t >> lx) mod nyb
+//   axis z: plane = t / G, G = 256/nzb lanes share a plane and stride its contiguous cells.
+// The 256/nrb partial sums of a plane are then added in a fixed (rotated, bank-conflict-free) order.
+template <typename T, int AXIS>
+__global__ void __launch_bounds__(kBT, 4)
+    k_block_moments_pow2(const T* __restrict__ rho, const T* __restrict__ ux, const T* __restrict__ uy,
+                         const T* __restrict__ uz, const fava_leaf_desc* __restrict__ leaves,
+                         const double* __restrict__ piv, int64_t nbins, int lx, int ly, int lz,
+                         double* __restrict__ partial) {
+    const int t = threadIdx.x;
+    const fava_leaf_desc leaf = leaves[blockIdx.x];
+    const int cells = 1 << (lx + ly + lz);
+    const int nrb = 1 << (AXIS == 0 ? lx : (AXIS == 1 ? ly : lz));
+    const int G = kBT / nrb;  // threads per plane
+    const int64_t base = leaf.block * (int64_t)cells;
+
+    int plane, e0, step, nit;
+    if (AXIS == 0) {
+        plane = t & (nrb - 1), e0 = t, step = kBT, nit = cells / kBT;
+    } else if (AXIS == 1) {
+        plane = (t >> lx) & (nrb - 1), e0 = t, step = kBT, nit = cells / kBT;
+    } else {
+        plane = t / G;
+        e0 = (plane << (lx + ly)) + (t - plane * G), step = G, nit = (1 << (lx + ly)) / G;
+    }
+    const int64_t pbin = leaf.ilo + (int64_t)plane * leaf.scale;
+    const double c0 = piv[pbin], c1 = piv[nbins + pbin], c2 = piv[2 * nbins + pbin];
+
+    Acc13 acc;
+    acc.clear();
+    const T* pr = rho + base + e0;
+    const T* px = ux + base + e0;
+    const T* py = uy + base + e0;
+    const T* pz = uz + base + e0;
+    int j = 0;
+    for (; j + 4 <= nit; j += 4) {
+        double vr[4], vx[4], vy[4], vz[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int o = (j + u) * step;
+            vr[u] = (double)__ldcs(pr + o);
+            vx[u] = (double)__ldcs(px + o);
+            vy[u] = (double)__ldcs(py + o);
+            vz[u] = (double)__ldcs(pz + o);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc.add(vr[u], vx[u], vy[u], vz[u], c0, c1, c2);
+    }
+    for (; j < nit; ++j) {
+        const int o = j * step;
+        acc.add((double)__ldcs(pr + o), (double)__ldcs(px + o), (double)__ldcs(py + o), (double)__ldcs(pz + o), c0,
+                c1, c2);
+    }
+
+    __shared__ double sm[kNMb][kBT];
+#pragma unroll
+    for (int m = 0; m < kNMb; ++m) sm[m][t] = acc.m[m];
+    __syncthreads();
+    for (int q = t; q < nrb * kNMb; q += kBT) {
+        const int m = q / nrb, p = q - m * nrb;
+        double s = 0.0;
+        for (int k = 0; k < G; ++k) {
+            const int g = (k + p) & (G - 1);  // rotation: lanes of a warp hit distinct banks
+            int tt;
+            if (AXIS == 0) tt = p + g * nrb;
+            else if (AXIS == 1) {
+                const int nx = 1 << lx;
+                tt = (g & (nx - 1)) + (p << lx) + ((g >> lx) << (lx + ly));
+            } else tt = p * G + g;
+            s += sm[m][tt];
+        }
+        partial[((int64_t)blockIdx.x * nrb + p) * kNMb + m] = s;
+    }
+}
+
+// ---- stage 1, generic path: any block shape; one warp per (leaf, plane) ------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kBT)
+    k_block_moments_generic(const T* __restrict__ rho, const T* __restrict__ ux, const T* __restrict__ uy,
+                            const T* __restrict__ uz, const fava_leaf_desc* __restrict__ leaves, int64_t nitems,
+                            const double* __restrict__ piv, int64_t nbins, int nxb, int nyb, int nzb, int axis,
+                            double* __restrict__ partial) {
+    const int lane = threadIdx.x & 31;
+    const int64_t item = (int64_t)blockIdx.x * (kBT / 32) + (threadIdx.x >> 5);
+    if (item >= nitems) return;
+    const int nrb = axis == 0 ? nxb : (axis == 1 ? nyb : nzb);
+    const int64_t l = item / nrb;
+    const int p = (int)(item - l * nrb);
+    const fava_leaf_desc leaf = leaves[l];
+    const int64_t base = leaf.block * ((int64_t)nxb * nyb * nzb);
+    const int64_t pbin = leaf.ilo + (int64_t)p * leaf.scale;
+    const double c0 = piv[pbin], c1 = piv[nbins + pbin], c2 = piv[2 * nbins + pbin];
+    const int pc = axis == 0 ? nyb * nzb : (axis == 1 ? nxb * nzb : nxb * nyb);
+    Acc13 acc;
+    acc.clear();
+    for (int c = lane; c < pc; c += 32) {
+        int64_t e;
+        if (axis == 0) e = (int64_t)c * nxb + p;                                  // c = z*nyb + y
+        else if (axis == 1) e = ((int64_t)(c / nxb) * nyb + p) * nxb + (c % nxb);  // c = z*nxb + x
+        else e = (int64_t)p * pc + c;
+        e += base;
+        acc.add((double)rho[e], (double)ux[e], (double)uy[e], (double)uz[e], c0, c1, c2);
+    }
+#pragma unroll
+    for (int m = 0; m < kNMb; ++m) {
+        const double s = warp_sum_fixed(acc.m[m]);
+        if (lane == 0) partial[item * kNMb + m] = s;
+    }
+}
+
+// ---- pivots: velocity at the first cell of the first item of every fine bin ---------------------------
+template <typename T>
+__global__ void k_block_pivots(const T* __restrict__ ux, const T* __restrict__ uy, const T* __restrict__ uz,
+                               const fava_leaf_desc* __restrict__ leaves, const int64_t* __restrict__ off,
+                               const int32_t* __restrict__ ent, int64_t nbins, int nxb, int nyb, int nzb, int axis,
+                               double* __restrict__ piv) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbins) return;
+    double c[3] = {0.0, 0.0, 0.0};
+    if (off[b + 1] > off[b]) {
+        const int nrb = axis == 0 ? nxb : (axis == 1 ? nyb : nzb);
+        const int64_t item = ent[off[b]];
+        const int64_t l = item / nrb;
+        const int64_t p = item - l * nrb;
+        const int64_t stride = axis == 0 ? 1 : (axis == 1 ? nxb : (int64_t)nxb * nyb);
+        const int64_t e = leaves[l].block * ((int64_t)nxb * nyb * nzb) + p * stride;
+        c[0] = (double)ux[e], c[1] = (double)uy[e], c[2] = (double)uz[e];
+    }
+    piv[b] = c[0], piv[nbins + b] = c[1], piv[2 * nbins + b] = c[2];
+}
+
+// ---- stage 2: items -> fine-bin moments ---------------------------------------------------------------
+constexpr int kCT = 128;
+__global__ void __launch_bounds__(kCT)
+    k_combine_items(const double* __restrict__ partial, const fava_leaf_desc* __restrict__ leaves,
+                    const int64_t* __restrict__ off, const int32_t* __restrict__ ent,
+                    const double* __restrict__ piv, int64_t nbins, int nrb, double plane_cells,
+                    double* __restrict__ mom) {
+    const int64_t b = blockIdx.x;
+    const int t = threadIdx.x;
+    const double cb[3] = {piv[b], piv[nbins + b], piv[2 * nbins + b]};
+    double acc[FAVA_NMOM];
+#pragma unroll
+    for (int m = 0; m < FAVA_NMOM; ++m) acc[m] = 0.0;
+    for (int64_t k = off[b] + t; k < off[b + 1]; k += kCT) {
+        const int64_t item = ent[k];
+        const int64_t l = item / nrb;
+        const int p = (int)(item - l * nrb);
+        const fava_leaf_desc leaf = leaves[l];
+        const int64_t pb = leaf.ilo + (int64_t)p * leaf.scale;
+        const double* q = partial + item * kNMb;
+        double e[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) e[i] = piv[i * nbins + pb] - cb[i];  // c_item - c_bin
+        const double s0 = q[0];
+        double srd[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) srd[i] = q[4 + i];
+        const double vf = leaf.vol_frac;
+        acc[0] += vf * s0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            acc[1 + i] += vf * (q[1 + i] + plane_cells * e[i]);
+            acc[4 + i] += vf * (srd[i] + e[i] * s0);
+        }
+        int kk = 7;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = i; j < 3; ++j, ++kk)
+                acc[kk] += vf * (q[kk] + e[i] * srd[j] + e[j] * srd[i] + e[i] * e[j] * s0);
+        acc[13] += vf * plane_cells;
+    }
+    __shared__ double sm[FAVA_NMOM][kCT / 32];
+    const int lane = t & 31, warp = t >> 5;
+#pragma unroll
+    for (int m = 0; m < FAVA_NMOM; ++m) {
+        const double s = warp_sum_fixed(acc[m]);
+        if (lane == 0) sm[m][warp] = s;
+    }
+    __syncthreads();
+    if (t < FAVA_NMOM) {
+        double s = sm[t][0];
+#pragma unroll
+        for (int w = 1; w < kCT / 32; ++w) s += sm[t][w];
+        mom[(int64_t)t * nbins + b] = s;
+    }
+}
+
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int ilog2_exact(int64_t v) {
+    if (v <= 0 || (v & (v - 1))) return -1;
+    int l = 0;
+    while ((int64_t(1) << l) < v) ++l;
+    return l;
+}
+
+struct ItemTables {
+    fava_leaf_desc* leaves = nullptr;
+    int64_t* off = nullptr;
+    int32_t* ent = nullptr;
+};
+
+// Host: CSR bin -> items (item = leaf*nrb + plane; leaf order preserved inside a bin), uploaded with the
+// leaf table into the context's table workspace.
+static int build_item_tables(fava_ctx* ctx, const fava_leaf_desc* h_leaves, int64_t nleaf, int nrb, int64_t nbins,
+                             cudaStream_t st, ItemTables* out) {
+    const int64_t nitems = nleaf * nrb;
+    std::vector<int64_t> off((size_t)nbins + 1, 0);
+    for (int64_t l = 0; l < nleaf; ++l) {
+        const fava_leaf_desc& d = h_leaves[l];
+        if (d.scale < 1 || d.ilo < 0 || d.ilo + (int64_t)nrb * d.scale > nbins || d.block < 0)
+            return set_error(FAVA_EINVAL, "block front end: leaf %lld (block %lld, ilo %lld, scale %d) "
+                             "does not fit %lld bins", (long long)l, (long long)d.block, (long long)d.ilo, d.scale,
+                             (long long)nbins);
+        for (int64_t b = d.ilo; b < d.ilo + (int64_t)nrb * d.scale; ++b) off[(size_t)b + 1]++;
+    }
+    for (int64_t b = 0; b < nbins; ++b) off[(size_t)b + 1] += off[(size_t)b];
+    const int64_t nent = off[(size_t)nbins];
+    if (nitems > INT32_MAX) return set_error(FAVA_EINVAL, "block front end: too many block planes");
+    std::vector<int32_t> ent((size_t)std::max<int64_t>(nent, 1));
+    {
+        std::vector<int64_t> cur(off.begin(), off.end() - 1);
+        for (int64_t l = 0; l < nleaf; ++l) {
+            const fava_leaf_desc& d = h_leaves[l];
+            for (int p = 0; p < nrb; ++p)
+                for (int s = 0; s < d.scale; ++s) ent[(size_t)cur[(size_t)(d.ilo + (int64_t)p * d.scale + s)]++] =
+                    (int32_t)(l * nrb + p);
+        }
+    }
+    const size_t b_leaves = sizeof(fava_leaf_desc) * (size_t)std::max<int64_t>(nleaf, 1);
+    const size_t b_off = sizeof(int64_t) * ((size_t)nbins + 1);
+    const size_t b_ent = sizeof(int32_t) * ent.size();
+    void* tab;
+    int rc = ctx_workspace(ctx, WS_TABLE, b_leaves + b_off + b_ent, &tab);
+    if (rc) return rc;
+    out->leaves = (fava_leaf_desc*)tab;
+    out->off = (int64_t*)((char*)tab + b_leaves);
+    out->ent = (int32_t*)((char*)tab + b_leaves + b_off);
+    // the vectors are pageable: cudaMemcpyAsync has staged them before it returns
+    if (nleaf) FAVA_CHECK_CUDA(cudaMemcpyAsync(out->leaves, h_leaves, sizeof(fava_leaf_desc) * nleaf, cudaMemcpyHostToDevice, st));
+    FAVA_CHECK_CUDA(cudaMemcpyAsync(out->off, off.data(), b_off, cudaMemcpyHostToDevice, st));
+    FAVA_CHECK_CUDA(cudaMemcpyAsync(out->ent, ent.data(), b_ent, cudaMemcpyHostToDevice, st));
+    return FAVA_OK;
+}
+
+template <typename T>
+static int run_blocks(fava_ctx* ctx, const T* rho, const T* ux, const T* uy, const T* uz, int64_t nzb, int64_t nyb,
+                      int64_t nxb, int axis, const fava_leaf_desc* h_leaves, int64_t nleaf, int64_t nbins,
+                      double* mom, double* piv, cudaStream_t st) {
+    const int nrb = (int)(axis == 0 ? nxb : (axis == 1 ? nyb : nzb));
+    const int64_t nitems = nleaf * nrb;
+    ItemTables tb;
+    int rc = build_item_tables(ctx, h_leaves, nleaf, nrb, nbins, st, &tb);
+    if (rc) return rc;
+    fava_leaf_desc* d_leaves = tb.leaves;
+    int64_t* d_off = tb.off;
+    int32_t* d_ent = tb.ent;
+
+    void* ws;
+    rc = ctx_workspace(ctx, WS_PARTIALS, sizeof(double) * kNMb * (size_t)std::max<int64_t>(nitems, 1), &ws);
+    if (rc) return rc;
+    double* partial = (double*)ws;
+
+    k_block_pivots<T><<<(unsigned)cdiv(nbins, 128), 128, 0, st>>>(ux, uy, uz, d_leaves, d_off, d_ent, nbins, (int)nxb,
+                                                                 (int)nyb, (int)nzb, axis, piv);
+    FAVA_LAUNCHED();
+    if (nleaf) {
+        const int lx = ilog2_exact(nxb), ly = ilog2_exact(nyb), lz = ilog2_exact(nzb);
+        const bool pow2 = lx >= 0 && ly >= 0 && lz >= 0 && nxb * nyb <= kBT && nxb * nyb * nzb >= kBT && nrb <= kBT &&
+                          (axis != 2 || (nxb * nyb) >= kBT / nzb);
+        if (pow2) {
+            const unsigned grid = (unsigned)nleaf;
+            if (axis == 0)
+                k_block_moments_pow2<T, 0><<<grid, kBT, 0, st>>>(rho, ux, uy, uz, d_leaves, piv, nbins, lx, ly, lz, partial);
+            else if (axis == 1)
+                k_block_moments_pow2<T, 1><<<grid, kBT, 0, st>>>(rho, ux, uy, uz, d_leaves, piv, nbins, lx, ly, lz, partial);
+            else
+                k_block_moments_pow2<T, 2><<<grid, kBT, 0, st>>>(rho, ux, uy, uz, d_leaves, piv, nbins, lx, ly, lz, partial);
+        } else {
+            k_block_moments_generic<T><<<(unsigned)cdiv(nitems, kBT / 32), kBT, 0, st>>>(
+                rho, ux, uy, uz, d_leaves, nitems, piv, nbins, (int)nxb, (int)nyb, (int)nzb, axis, partial);
+        }
+        FAVA_LAUNCHED();
+    }
+    const double plane_cells = (double)(nxb * nyb * nzb / nrb);
+    k_combine_items<<<(unsigned)nbins, kCT, 0, st>>>(partial, d_leaves, d_off, d_ent, piv, nbins, nrb, plane_cells, mom);
+    FAVA_LAUNCHED();
+    return FAVA_OK;
+}
+
+
+// ---- single-field plane integral of a block dataset (reference slice_integral, _flash.py:1451-1504) ---
+template <typename T>
+__global__ void __launch_bounds__(kBT)
+    k_block_sum_generic(const T* __restrict__ f, const fava_leaf_desc* __restrict__ leaves, int64_t nitems, int nxb,
+                        int nyb, int nzb, int axis, double* __restrict__ partial) {
+    const int lane = threadIdx.x & 31;
+    const int64_t item = (int64_t)blockIdx.x * (kBT / 32) + (threadIdx.x >> 5);
+    if (item >= nitems) return;
+    const int nrb = axis == 0 ? nxb : (axis == 1 ? nyb : nzb);
+    const int64_t l = item / nrb;
+    const int p = (int)(item - l * nrb);
+    const int64_t base = leaves[l].block * ((int64_t)nxb * nyb * nzb);
+    const int pc = axis == 0 ? nyb * nzb : (axis == 1 ? nxb * nzb : nxb * nyb);
+    double acc = 0.0;
+    for (int c = lane; c < pc; c += 32) {
+        int64_t e;
+        if (axis == 0) e = (int64_t)c * nxb + p;
+        else if (axis == 1) e = ((int64_t)(c / nxb) * nyb + p) * nxb + (c % nxb);
+        else e = (int64_t)p * pc + c;
+        acc += (double)f[base + e];
+    }
+    acc = warp_sum_fixed(acc);
+    if (lane == 0) partial[item] = acc;
+}
+
+__global__ void __launch_bounds__(kCT)
+    k_combine_sums(const double* __restrict__ partial, const fava_leaf_desc* __restrict__ leaves,
+                   const int64_t* __restrict__ off, const int32_t* __restrict__ ent, int nrb, double* __restrict__ out) {
+    const int64_t b = blockIdx.x;
+    const int t = threadIdx.x;
+    double acc = 0.0;
+    for (int64_t k = off[b] + t; k < off[b + 1]; k += kCT) {
+        const int64_t item = ent[k];
+        acc += leaves[item / nrb].vol_frac * partial[item];
+    }
+    __shared__ double sm[kCT / 32];
+    const double s = warp_sum_fixed(acc);
+    if ((t & 31) == 0) sm[t >> 5] = s;
+    __syncthreads();
+    if (t == 0) {
+        double r = sm[0];
+#pragma unroll
+        for (int w = 1; w < kCT / 32; ++w) r += sm[w];
+        out[b] = r;
+    }
+}
+
+template <typename T>
+static int run_block_sum(fava_ctx* ctx, const T* f, int64_t nzb, int64_t nyb, int64_t nxb, int axis,
+                         const fava_leaf_desc* h_leaves, int64_t nleaf, int64_t nbins, double* out, cudaStream_t st) {
+    const int nrb = (int)(axis == 0 ? nxb : (axis == 1 ? nyb : nzb));
+    const int64_t nitems = nleaf * nrb;
+    ItemTables tb;
+    int rc = build_item_tables(ctx, h_leaves, nleaf, nrb, nbins, st, &tb);
+    if (rc) return rc;
+    void* ws;
+    rc = ctx_workspace(ctx, WS_PARTIALS, sizeof(double) * (size_t)std::max<int64_t>(nitems, 1), &ws);
+    if (rc) return rc;
+    if (nitems) {
+        k_block_sum_generic<T><<<(unsigned)cdiv(nitems, kBT / 32), kBT, 0, st>>>(f, tb.leaves, nitems, (int)nxb, (int)nyb,
+                                                                               (int)nzb, axis, (double*)ws);
+        FAVA_LAUNCHED();
+    }
+    k_combine_sums<<<(unsigned)nbins, kCT, 0, st>>>((const double*)ws, tb.leaves, tb.off, tb.ent, nrb, out);
+    FAVA_LAUNCHED();
+    return FAVA_OK;
+}
+
+}  // namespace fava
+
+using namespace fava;
+
+extern "C" int fava_plane_moments_blocks(fava_ctx* ctx, const void* d_rho, const void* d_ux, const void* d_uy,
+                                         const void* d_uz, int dtype, int64_t nzb, int64_t nyb, int64_t nxb,
+                                         int axis, const fava_leaf_desc* h_leaves, int64_t nleaf, int64_t nbins,
+                                         double* d_moments, double* d_pivots, void* stream) {
+    FAVA_REQUIRE(ctx && d_moments && d_pivots, "fava_plane_moments_blocks: NULL argument");
+    FAVA_REQUIRE(nleaf >= 0 && (nleaf == 0 || (h_leaves && d_rho && d_ux && d_uy && d_uz)),
+                 "fava_plane_moments_blocks: NULL field or leaf table");
+    FAVA_REQUIRE(nzb > 0 && nyb > 0 && nxb > 0 && nzb * nyb * nxb < (int64_t(1) << 30),
+                 "fava_plane_moments_blocks: bad block shape %lldx%lldx%lld", (long long)nzb, (long long)nyb,
+                 (long long)nxb);
+    FAVA_REQUIRE(axis >= 0 && axis <= 2, "fava_plane_moments_blocks: axis %d not in 0..2", axis);
+    FAVA_REQUIRE(dtype == FAVA_F32 || dtype == FAVA_F64, "fava_plane_moments_blocks: bad dtype %d", dtype);
+    FAVA_REQUIRE(nbins > 0 && nbins < (int64_t(1) << 31), "fava_plane_moments_blocks: bad bin count %lld", (long long)nbins);
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == FAVA_F64)
+        return run_blocks<double>(ctx, (const double*)d_rho, (const double*)d_ux, (const double*)d_uy,
+                                  (const double*)d_uz, nzb, nyb, nxb, axis, h_leaves, nleaf, nbins, d_moments,
+                                  d_pivots, st);
+    return run_blocks<float>(ctx, (const float*)d_rho, (const float*)d_ux, (const float*)d_uy, (const float*)d_uz, nzb,
+                             nyb, nxb, axis, h_leaves, nleaf, nbins, d_moments, d_pivots, st);
+}
+
+extern "C" int fava_plane_sum_blocks(fava_ctx* ctx, const void* d_field, int dtype, int64_t nzb, int64_t nyb,
+                                     int64_t nxb, int axis, const fava_leaf_desc* h_leaves, int64_t nleaf,
+                                     int64_t nbins, double* d_out, void* stream) {
+    FAVA_REQUIRE(ctx && d_out, "fava_plane_sum_blocks: NULL argument");
+    FAVA_REQUIRE(nleaf >= 0 && (nleaf == 0 || (h_leaves && d_field)), "fava_plane_sum_blocks: NULL field or leaf table");
+    FAVA_REQUIRE(nzb > 0 && nyb > 0 && nxb > 0 && nzb * nyb * nxb < (int64_t(1) << 30),
+                 "fava_plane_sum_blocks: bad block shape");
+    FAVA_REQUIRE(axis >= 0 && axis <= 2, "fava_plane_sum_blocks: axis %d not in 0..2", axis);
+    FAVA_REQUIRE(dtype == FAVA_F32 || dtype == FAVA_F64, "fava_plane_sum_blocks: bad dtype %d", dtype);
+    FAVA_REQUIRE(nbins > 0 && nbins < (int64_t(1) << 31), "fava_plane_sum_blocks: bad bin count");
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == FAVA_F64)
+        return run_block_sum<double>(ctx, (const double*)d_field, nzb, nyb, nxb, axis, h_leaves, nleaf, nbins, d_out, st);
+    return run_block_sum<float>(ctx, (const float*)d_field, nzb, nyb, nxb, axis, h_leaves, nleaf, nbins, d_out, st);
+}

@@ -63,6 +63,7 @@ struct fava_ctx {
     size_t ws_bytes[fava::WS_COUNT] = {};
     // cuFFT plans keyed by (kind, a, b, c)
     std::map<std::tuple<int, int64_t, int64_t, int64_t>, cufftHandle> plans;
+    std::map<std::tuple<int, int64_t, int64_t, int64_t>, size_t> plan_work;  // work-area bytes per plan
     fava::Staging* staging = nullptr;
 };
 

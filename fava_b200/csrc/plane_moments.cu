@@ -24,36 +24,59 @@ constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kNM = FAVA_NMOM - 1;  // 13 accumulated moments; row 13 (W) is analytic for dense input
 
+// NM = 13: the pivoted moment set; NM = 1: a plain plane sum of the first field (slice_integral).
+template <int NM>
 struct Acc {
-    double m[kNM];
+    double m[NM];
     __device__ __forceinline__ void clear() {
 #pragma unroll
-        for (int i = 0; i < kNM; ++i) m[i] = 0.0;
+        for (int i = 0; i < NM; ++i) m[i] = 0.0;
     }
     __device__ __forceinline__ void add(double r, double x, double y, double z, double c0, double c1,
                                         double c2) {
+        if constexpr (NM == 1) {
+            m[0] += r;
+            return;
+        }
         const double dx = x - c0, dy = y - c1, dz = z - c2;
         const double rx = r * dx, ry = r * dy, rz = r * dz;
-        m[0] += r;
-        m[1] += dx;
-        m[2] += dy;
-        m[3] += dz;
-        m[4] += rx;
-        m[5] += ry;
-        m[6] += rz;
-        m[7] = fma(rx, dx, m[7]);
-        m[8] = fma(rx, dy, m[8]);
-        m[9] = fma(rx, dz, m[9]);
-        m[10] = fma(ry, dy, m[10]);
-        m[11] = fma(ry, dz, m[11]);
-        m[12] = fma(rz, dz, m[12]);
+        if constexpr (NM > 1) {
+            m[0] += r;
+            m[1] += dx;
+            m[2] += dy;
+            m[3] += dz;
+            m[4] += rx;
+            m[5] += ry;
+            m[6] += rz;
+            m[7] = fma(rx, dx, m[7]);
+            m[8] = fma(rx, dy, m[8]);
+            m[9] = fma(rx, dz, m[9]);
+            m[10] = fma(ry, dy, m[10]);
+            m[11] = fma(ry, dz, m[11]);
+            m[12] = fma(rz, dz, m[12]);
+        }
     }
 };
+
+// loads the velocity operands only when they are used
+template <typename T, int V, int NM>
+__device__ __forceinline__ void load4(const T* rho, const T* ux, const T* uy, const T* uz, int64_t off, double (&vr)[V],
+                                      double (&vx)[V], double (&vy)[V], double (&vz)[V]) {
+    VecLoad<T, V>::ld(rho + off, vr);
+    if constexpr (NM > 1) {
+        VecLoad<T, V>::ld(ux + off, vx);
+        VecLoad<T, V>::ld(uy + off, vy);
+        VecLoad<T, V>::ld(uz + off, vz);
+    } else {
+#pragma unroll
+        for (int v = 0; v < V; ++v) vx[v] = vy[v] = vz[v] = 0.0;
+    }
+}
 
 // ---- axis 0 (x, the fastest index): column sums -----------------------------------------------
 // A warp owns a 32*V-column strip, a CTA's 8 warps take 8 consecutive rows per step; every thread
 // keeps 13*V accumulators for its V columns.  grid = (column strips, row chunks).
-template <typename T, int V, int U>
+template <typename T, int V, int U, int NM>
 __global__ void __launch_bounds__(kThreads, 2)
     k_moments_cols(const T* __restrict__ rho, const T* __restrict__ ux, const T* __restrict__ uy,
                    const T* __restrict__ uz, int64_t nrows, int64_t nx, const double* __restrict__ piv,
@@ -64,7 +87,7 @@ __global__ void __launch_bounds__(kThreads, 2)
     const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
     const int64_t r1 = min(nrows, r0 + rows_per_chunk);
 
-    Acc acc[V];
+    Acc<NM> acc[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) acc[v].clear();
 
@@ -73,7 +96,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
-            for (int v = 0; v < V; ++v) c[i][v] = piv[i * nx + x0 + v];
+            for (int v = 0; v < V; ++v) c[i][v] = NM > 1 ? piv[i * nx + x0 + v] : 0.0;
 
         int64_t r = r0 + warp;
         for (; r + (int64_t)(U - 1) * kWarps < r1; r += (int64_t)U * kWarps) {
@@ -81,10 +104,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int64_t off = (r + (int64_t)u * kWarps) * nx + x0;
-                VecLoad<T, V>::ld(rho + off, vr[u]);
-                VecLoad<T, V>::ld(ux + off, vx[u]);
-                VecLoad<T, V>::ld(uy + off, vy[u]);
-                VecLoad<T, V>::ld(uz + off, vz[u]);
+                load4<T, V, NM>(rho, ux, uy, uz, off, vr[u], vx[u], vy[u], vz[u]);
             }
 #pragma unroll
             for (int u = 0; u < U; ++u)
@@ -95,10 +115,7 @@ __global__ void __launch_bounds__(kThreads, 2)
         for (; r < r1; r += kWarps) {
             double vr[V], vx[V], vy[V], vz[V];
             const int64_t off = r * nx + x0;
-            VecLoad<T, V>::ld(rho + off, vr);
-            VecLoad<T, V>::ld(ux + off, vx);
-            VecLoad<T, V>::ld(uy + off, vy);
-            VecLoad<T, V>::ld(uz + off, vz);
+            load4<T, V, NM>(rho, ux, uy, uz, off, vr, vx, vy, vz);
 #pragma unroll
             for (int v = 0; v < V; ++v) acc[v].add(vr[v], vx[v], vy[v], vz[v], c[0][v], c[1][v], c[2][v]);
         }
@@ -106,9 +123,9 @@ __global__ void __launch_bounds__(kThreads, 2)
 
     // fixed-order sum over the CTA's 8 warps, one moment at a time through 2 KB * V of smem
     __shared__ double sm[kWarps][32 * V];
-    double* out = partial + (int64_t)blockIdx.y * kNM * nx;
+    double* out = partial + (int64_t)blockIdx.y * NM * nx;
 #pragma unroll
-    for (int m = 0; m < kNM; ++m) {
+    for (int m = 0; m < NM; ++m) {
 #pragma unroll
         for (int v = 0; v < V; ++v) sm[warp][lane * V + v] = acc[v].m[m];
         __syncthreads();
@@ -130,7 +147,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 // b*bin_stride + j*row_stride (axis y: bin_stride=nx, row_stride=ny*nx; axis z: the plane is
 // contiguous).  grid = (bins, row chunks); a CTA streams whole rows (4 KB per step for fp64) with
 // 13 accumulators per thread, then block-reduces in a fixed pattern.
-template <typename T, int V, int U>
+template <typename T, int V, int U, int NM>
 __global__ void __launch_bounds__(kThreads, 2)
     k_moments_rows(const T* __restrict__ rho, const T* __restrict__ ux, const T* __restrict__ uy,
                    const T* __restrict__ uz, int64_t row_len, int64_t bin_stride, int64_t row_stride,
@@ -141,10 +158,11 @@ __global__ void __launch_bounds__(kThreads, 2)
     const int rpi = kThreads / lanes_x;
     const int64_t j0 = (int64_t)blockIdx.y * rows_per_chunk;
     const int64_t j1 = min(rows_per_bin, j0 + rows_per_chunk);
-    const double c0 = piv[bin], c1 = piv[nbins + bin], c2 = piv[2 * nbins + bin];
+    const double c0 = NM > 1 ? piv[bin] : 0.0, c1 = NM > 1 ? piv[nbins + bin] : 0.0,
+                 c2 = NM > 1 ? piv[2 * nbins + bin] : 0.0;
     const int64_t base = bin * bin_stride;
 
-    Acc acc;
+    Acc<NM> acc;
     acc.clear();
 
     for (int64_t xv = (int64_t)tx * V; xv < row_len; xv += (int64_t)lanes_x * V) {
@@ -154,10 +172,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int64_t off = base + (j + (int64_t)u * rpi) * row_stride + xv;
-                VecLoad<T, V>::ld(rho + off, vr[u]);
-                VecLoad<T, V>::ld(ux + off, vx[u]);
-                VecLoad<T, V>::ld(uy + off, vy[u]);
-                VecLoad<T, V>::ld(uz + off, vz[u]);
+                load4<T, V, NM>(rho, ux, uy, uz, off, vr[u], vx[u], vy[u], vz[u]);
             }
 #pragma unroll
             for (int u = 0; u < U; ++u)
@@ -167,41 +182,39 @@ __global__ void __launch_bounds__(kThreads, 2)
         for (; j < j1; j += rpi) {
             double vr[V], vx[V], vy[V], vz[V];
             const int64_t off = base + j * row_stride + xv;
-            VecLoad<T, V>::ld(rho + off, vr);
-            VecLoad<T, V>::ld(ux + off, vx);
-            VecLoad<T, V>::ld(uy + off, vy);
-            VecLoad<T, V>::ld(uz + off, vz);
+            load4<T, V, NM>(rho, ux, uy, uz, off, vr, vx, vy, vz);
 #pragma unroll
             for (int v = 0; v < V; ++v) acc.add(vr[v], vx[v], vy[v], vz[v], c0, c1, c2);
         }
     }
 
-    __shared__ double sm[kNM][kWarps];
+    __shared__ double sm[NM][kWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int m = 0; m < kNM; ++m) {
+    for (int m = 0; m < NM; ++m) {
         const double s = warp_sum_fixed(acc.m[m]);
         if (lane == 0) sm[m][warp] = s;
     }
     __syncthreads();
-    if (threadIdx.x < kNM) {
+    if (threadIdx.x < NM) {
         double s = sm[threadIdx.x][0];
 #pragma unroll
         for (int w = 1; w < kWarps; ++w) s += sm[threadIdx.x][w];
-        partial[((int64_t)blockIdx.y * kNM + threadIdx.x) * nbins + bin] = s;
+        partial[((int64_t)blockIdx.y * NM + threadIdx.x) * nbins + bin] = s;
     }
 }
 
 // ---- level 2: partials -> moments --------------------------------------------------------------
-__global__ void k_reduce_partials(const double* __restrict__ partial, int nchunk, int64_t nbins,
+// nm = moments held per chunk; nrows = rows of `mom` (nm, or nm+1 when the analytic W row is appended)
+__global__ void k_reduce_partials(const double* __restrict__ partial, int nchunk, int64_t nbins, int nm, int nrows,
                                   double* __restrict__ mom, int accumulate, double cells_per_bin) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (int64_t)FAVA_NMOM * nbins) return;
+    if (idx >= (int64_t)nrows * nbins) return;
     const int64_t m = idx / nbins, b = idx - m * nbins;
     double s;
-    if (m < kNM) {
+    if (m < nm) {
         s = 0.0;
-        for (int c = 0; c < nchunk; ++c) s += partial[((int64_t)c * kNM + m) * nbins + b];
+        for (int c = 0; c < nchunk; ++c) s += partial[((int64_t)c * nm + m) * nbins + b];
     } else {
         s = cells_per_bin;
     }
@@ -290,7 +303,7 @@ static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b
 
 static bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
-template <typename T, int V, int U>
+template <typename T, int V, int U, int NM>
 static int launch_dense(fava_ctx* ctx, const T* rho, const T* ux, const T* uy, const T* uz, int64_t nz,
                         int64_t ny, int64_t nx, int axis, const double* piv, double* mom, int accumulate,
                         cudaStream_t st) {
@@ -306,11 +319,11 @@ static int launch_dense(fava_ctx* ctx, const T* rho, const T* ux, const T* uy, c
         int64_t rpc = round_up(ceil_div(nrows, want), step);
         nchunk = (int)ceil_div(nrows, rpc);
         void* ws;
-        int rc = ctx_workspace(ctx, WS_PARTIALS, sizeof(double) * (size_t)nchunk * kNM * nbins, &ws);
+        int rc = ctx_workspace(ctx, WS_PARTIALS, sizeof(double) * (size_t)nchunk * NM * nbins, &ws);
         if (rc) return rc;
         partial = (double*)ws;
         dim3 grid((unsigned)strips, (unsigned)nchunk);
-        k_moments_cols<T, V, U><<<grid, kThreads, 0, st>>>(rho, ux, uy, uz, nrows, nx, piv, partial, rpc);
+        k_moments_cols<T, V, U, NM><<<grid, kThreads, 0, st>>>(rho, ux, uy, uz, nrows, nx, piv, partial, rpc);
         FAVA_LAUNCHED();
     } else {
         int64_t row_len, bin_stride, row_stride, rows_per_bin;
@@ -332,22 +345,24 @@ static int launch_dense(fava_ctx* ctx, const T* rho, const T* ux, const T* uy, c
         int64_t rpc = round_up(ceil_div(rows_per_bin, want), step);
         nchunk = (int)ceil_div(rows_per_bin, rpc);
         void* ws;
-        int rc = ctx_workspace(ctx, WS_PARTIALS, sizeof(double) * (size_t)nchunk * kNM * nbins, &ws);
+        int rc = ctx_workspace(ctx, WS_PARTIALS, sizeof(double) * (size_t)nchunk * NM * nbins, &ws);
         if (rc) return rc;
         partial = (double*)ws;
         dim3 grid((unsigned)nbins, (unsigned)nchunk);
-        k_moments_rows<T, V, U><<<grid, kThreads, 0, st>>>(rho, ux, uy, uz, row_len, bin_stride, row_stride,
+        k_moments_rows<T, V, U, NM><<<grid, kThreads, 0, st>>>(rho, ux, uy, uz, row_len, bin_stride, row_stride,
                                                           rows_per_bin, rpc, piv, nbins, partial, lanes_x);
         FAVA_LAUNCHED();
     }
-    const int64_t n = (int64_t)FAVA_NMOM * nbins;
+    const int nrows = NM > 1 ? FAVA_NMOM : 1;
+    const int64_t n = (int64_t)nrows * nbins;
     const double cells = (double)(nz * ny * nx / nbins);
-    k_reduce_partials<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(partial, nchunk, nbins, mom, accumulate, cells);
+    k_reduce_partials<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(partial, nchunk, nbins, NM, nrows, mom, accumulate,
+                                                                 cells);
     FAVA_LAUNCHED();
     return FAVA_OK;
 }
 
-template <typename T, int U>
+template <typename T, int U, int NM>
 static int dispatch_dense(fava_ctx* ctx, const void* rho, const void* ux, const void* uy, const void* uz,
                           int64_t nz, int64_t ny, int64_t nx, int axis, const double* piv, double* mom,
                           int accumulate, cudaStream_t st) {
@@ -355,9 +370,9 @@ static int dispatch_dense(fava_ctx* ctx, const void* rho, const void* ux, const 
     const bool vec = (nx % 2 == 0) && aligned_to(rho, va) && aligned_to(ux, va) && aligned_to(uy, va) &&
                      aligned_to(uz, va);
     if (vec)
-        return launch_dense<T, 2, U>(ctx, (const T*)rho, (const T*)ux, (const T*)uy, (const T*)uz, nz, ny, nx,
+        return launch_dense<T, 2, U, NM>(ctx, (const T*)rho, (const T*)ux, (const T*)uy, (const T*)uz, nz, ny, nx,
                                      axis, piv, mom, accumulate, st);
-    return launch_dense<T, 1, U>(ctx, (const T*)rho, (const T*)ux, (const T*)uy, (const T*)uz, nz, ny, nx, axis,
+    return launch_dense<T, 1, U, NM>(ctx, (const T*)rho, (const T*)ux, (const T*)uy, (const T*)uz, nz, ny, nx, axis,
                                  piv, mom, accumulate, st);
 }
 
@@ -401,10 +416,25 @@ int fava_plane_moments(fava_ctx* ctx, const void* d_rho, const void* d_ux, const
     DeviceGuard g(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == FAVA_F64)
-        return dispatch_dense<double, 4>(ctx, d_rho, d_ux, d_uy, d_uz, nz, ny, nx, axis, d_pivots, d_moments,
+        return dispatch_dense<double, 4, kNM>(ctx, d_rho, d_ux, d_uy, d_uz, nz, ny, nx, axis, d_pivots, d_moments,
                                          accumulate, st);
-    return dispatch_dense<float, 8>(ctx, d_rho, d_ux, d_uy, d_uz, nz, ny, nx, axis, d_pivots, d_moments,
+    return dispatch_dense<float, 8, kNM>(ctx, d_rho, d_ux, d_uy, d_uz, nz, ny, nx, axis, d_pivots, d_moments,
                                     accumulate, st);
+}
+
+int fava_plane_sum(fava_ctx* ctx, const void* d_field, int dtype, int64_t nz, int64_t ny, int64_t nx, int axis,
+                   double* d_out, void* stream) {
+    FAVA_REQUIRE(ctx && d_field && d_out, "fava_plane_sum: NULL argument");
+    FAVA_REQUIRE(nz > 0 && ny > 0 && nx > 0, "fava_plane_sum: empty array");
+    FAVA_REQUIRE(axis >= 0 && axis <= 2, "fava_plane_sum: axis %d not in 0..2", axis);
+    FAVA_REQUIRE(dtype == FAVA_F32 || dtype == FAVA_F64, "fava_plane_sum: bad dtype %d", dtype);
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    // same streaming kernels as the moment pass with one accumulator; only the first operand is read
+    if (dtype == FAVA_F64)
+        return dispatch_dense<double, 4, 1>(ctx, d_field, d_field, d_field, d_field, nz, ny, nx, axis, nullptr, d_out,
+                                            0, st);
+    return dispatch_dense<float, 8, 1>(ctx, d_field, d_field, d_field, d_field, nz, ny, nx, axis, nullptr, d_out, 0, st);
 }
 
 int fava_moments_repivot(fava_ctx* ctx, double* d_moments, const double* d_piv_old, const double* d_piv_new,

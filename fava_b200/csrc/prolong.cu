@@ -1,0 +1,149 @@
+// K3 — AMR -> uniform prolongation (piecewise-constant injection) through a block-index table.
+//
+// Replaces the gather of FLASH.from_amr (reference fava/mesh/FLASH/_flash.py:1262-1321): a Python dict
+// with one entry per fine cell, mapping[(I,J,K)] = (leaf,i,j,k), built by triple loops (~8 us/cell)
+// and replayed per field (~0.8 us/cell).  Here the host turns the selected-leaf list (built with the
+// reference's integer arithmetic, _flash.py:1000-1022 / :1157-1199) into a lattice table
+//   tile (X/nxb, Y/nyb, Z/nzb) of the fine grid  ->  index of the leaf that owns it
+// (leaves are written in list order, so a later leaf overwrites an earlier one exactly like the dict
+// does, and tiles nobody owns stay -1 => 0.0 as in_data[...] = 0.0, :1258).  The kernel is a pure
+// gather: one thread per pair of fine cells, source cell = (fine - corner) / scale, coalesced 16 B
+// stores of the fp64 result in FILE order [Z][Y][X].  Bit-exact (f32 -> f64 widening is exact).
+// Traffic: every selected source cell is read once from HBM (repeats hit L1/L2), 8 B written per cell.
+#include <vector>
+
+#include "common.cuh"
+
+namespace fava {
+
+struct ProlongGeom {
+    int nxb, nyb, nzb;     // block shape
+    int sx, sy, sz;        // lattice shift: tile t covers fine cells [t*nb + s - nb, ...)
+    int tx, ty, tz;        // table dims
+    int64_t NX, NY, NZ;    // output dims
+};
+
+template <typename T>
+__device__ __forceinline__ double prolong_cell(const T* __restrict__ blocks, const fava_prolong_leaf* __restrict__ leaves,
+                                               const int32_t* __restrict__ table, const ProlongGeom& g, int64_t X,
+                                               int64_t Y, int64_t Z) {
+    const int tx = (int)((X - g.sx + g.nxb) / g.nxb);
+    const int ty = (int)((Y - g.sy + g.nyb) / g.nyb);
+    const int tz = (int)((Z - g.sz + g.nzb) / g.nzb);
+    const int32_t l = table[((int64_t)tz * g.ty + ty) * g.tx + tx];
+    if (l < 0) return 0.0;
+    const fava_prolong_leaf leaf = leaves[l];
+    const int i = (int)((X - leaf.off[0]) / leaf.scale);
+    const int j = (int)((Y - leaf.off[1]) / leaf.scale);
+    const int k = (int)((Z - leaf.off[2]) / leaf.scale);
+    return (double)blocks[((leaf.block * g.nzb + k) * g.nyb + j) * (int64_t)g.nxb + i];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+    k_prolong(const T* __restrict__ blocks, const fava_prolong_leaf* __restrict__ leaves,
+              const int32_t* __restrict__ table, ProlongGeom g, double* __restrict__ out) {
+    const int64_t row = blockIdx.y + (int64_t)blockIdx.z * gridDim.y;  // row = Z*NY + Y
+    if (row >= g.NZ * g.NY) return;
+    const int64_t Z = row / g.NY, Y = row - Z * g.NY;
+    double* orow = out + row * g.NX;
+    const bool vec = ((g.NX & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    for (int64_t X = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; X < g.NX;
+         X += (int64_t)gridDim.x * blockDim.x * 2) {
+        const double a = prolong_cell(blocks, leaves, table, g, X, Y, Z);
+        if (X + 1 < g.NX) {
+            const double b = prolong_cell(blocks, leaves, table, g, X + 1, Y, Z);
+            if (vec) __stcs(reinterpret_cast<double2*>(orow + X), make_double2(a, b));
+            else orow[X] = a, orow[X + 1] = b;
+        } else {
+            orow[X] = a;
+        }
+    }
+}
+
+static inline int pmod(int64_t a, int64_t n) { return (int)(((a % n) + n) % n); }
+static inline int64_t cdivp(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+template <typename T>
+static int run_prolong(fava_ctx* ctx, const T* blocks, int64_t nzb, int64_t nyb, int64_t nxb,
+                       const fava_prolong_leaf* h_leaves, int64_t nleaf, int64_t NZ, int64_t NY, int64_t NX,
+                       double* out, cudaStream_t st) {
+    ProlongGeom g;
+    g.nxb = (int)nxb, g.nyb = (int)nyb, g.nzb = (int)nzb;
+    g.NX = NX, g.NY = NY, g.NZ = NZ;
+    g.sx = g.sy = g.sz = 0;
+    if (nleaf) {
+        g.sx = pmod(h_leaves[0].off[0], nxb);
+        g.sy = pmod(h_leaves[0].off[1], nyb);
+        g.sz = pmod(h_leaves[0].off[2], nzb);
+    }
+    g.tx = (int)cdivp(NX - g.sx, nxb) + 1;
+    g.ty = (int)cdivp(NY - g.sy, nyb) + 1;
+    g.tz = (int)cdivp(NZ - g.sz, nzb) + 1;
+    const int64_t ntile = (int64_t)g.tx * g.ty * g.tz;
+    std::vector<int32_t> table((size_t)ntile, -1);
+    for (int64_t l = 0; l < nleaf; ++l) {
+        const fava_prolong_leaf& d = h_leaves[l];
+        if (d.scale < 1 || d.block < 0)
+            return set_error(FAVA_EINVAL, "fava_prolong: leaf %lld has scale %d / block %lld", (long long)l, d.scale,
+                             (long long)d.block);
+        if (pmod(d.off[0], nxb) != g.sx || pmod(d.off[1], nyb) != g.sy || pmod(d.off[2], nzb) != g.sz)
+            return set_error(FAVA_EINVAL, "fava_prolong: leaf %lld corner (%d,%d,%d) is not on the block lattice",
+                             (long long)l, d.off[0], d.off[1], d.off[2]);
+        // tiles covered by the leaf, clipped to the table
+        int64_t lo[3], hi[3];
+        const int dims[3] = {g.tx, g.ty, g.tz};
+        bool empty = false;
+        for (int a = 0; a < 3; ++a) {
+            // off may be far negative: floor division
+            const int64_t nb = a == 0 ? nxb : (a == 1 ? nyb : nzb);
+            const int64_t num = (int64_t)d.off[a] - (a == 0 ? g.sx : (a == 1 ? g.sy : g.sz)) + nb;
+            const int64_t first = num >= 0 ? num / nb : -((-num + nb - 1) / nb);
+            lo[a] = std::max<int64_t>(first, 0);
+            hi[a] = std::min<int64_t>(first + d.scale, dims[a]);
+            if (hi[a] <= lo[a]) empty = true;
+        }
+        if (empty) continue;
+        for (int64_t z = lo[2]; z < hi[2]; ++z)
+            for (int64_t y = lo[1]; y < hi[1]; ++y)
+                for (int64_t x = lo[0]; x < hi[0]; ++x) table[(size_t)((z * g.ty + y) * g.tx + x)] = (int32_t)l;
+    }
+    const size_t b_leaves = sizeof(fava_prolong_leaf) * (size_t)std::max<int64_t>(nleaf, 1);
+    const size_t b_table = sizeof(int32_t) * (size_t)ntile;
+    void* tab;
+    int rc = ctx_workspace(ctx, WS_TABLE, b_leaves + b_table, &tab);
+    if (rc) return rc;
+    auto* d_leaves = (fava_prolong_leaf*)tab;
+    auto* d_table = (int32_t*)((char*)tab + b_leaves);
+    if (nleaf) FAVA_CHECK_CUDA(cudaMemcpyAsync(d_leaves, h_leaves, sizeof(fava_prolong_leaf) * nleaf, cudaMemcpyHostToDevice, st));
+    FAVA_CHECK_CUDA(cudaMemcpyAsync(d_table, table.data(), b_table, cudaMemcpyHostToDevice, st));
+
+    const int64_t rows = NZ * NY;
+    const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdivp(NX, 512), 64));
+    const unsigned gy = (unsigned)std::min<int64_t>(rows, 32768);
+    const unsigned gz = (unsigned)cdivp(rows, gy);
+    k_prolong<T><<<dim3(gx, gy, gz), 256, 0, st>>>(blocks, d_leaves, d_table, g, out);
+    FAVA_LAUNCHED();
+    return FAVA_OK;
+}
+
+}  // namespace fava
+
+using namespace fava;
+
+extern "C" int fava_prolong(fava_ctx* ctx, const void* d_blocks, int dtype, int64_t nzb, int64_t nyb, int64_t nxb,
+                            const fava_prolong_leaf* h_leaves, int64_t nleaf, int64_t NZ, int64_t NY, int64_t NX,
+                            double* d_out, void* stream) {
+    FAVA_REQUIRE(ctx && d_out, "fava_prolong: NULL argument");
+    FAVA_REQUIRE(nleaf >= 0 && (nleaf == 0 || (h_leaves && d_blocks)), "fava_prolong: NULL block data or leaf table");
+    FAVA_REQUIRE(nzb > 0 && nyb > 0 && nxb > 0, "fava_prolong: bad block shape");
+    FAVA_REQUIRE(NZ > 0 && NY > 0 && NX > 0, "fava_prolong: empty output %lldx%lldx%lld", (long long)NZ,
+                 (long long)NY, (long long)NX);
+    FAVA_REQUIRE(dtype == FAVA_F32 || dtype == FAVA_F64, "fava_prolong: bad dtype %d", dtype);
+    FAVA_REQUIRE(nleaf < INT32_MAX, "fava_prolong: too many leaves");
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == FAVA_F64)
+        return run_prolong<double>(ctx, (const double*)d_blocks, nzb, nyb, nxb, h_leaves, nleaf, NZ, NY, NX, d_out, st);
+    return run_prolong<float>(ctx, (const float*)d_blocks, nzb, nyb, nxb, h_leaves, nleaf, NZ, NY, NX, d_out, st);
+}

@@ -1,0 +1,436 @@
+// Kinetic-energy spectrum on sm_100a — replaces FlashUniform.kinetic_energy_spectra
+// (reference fava/mesh/FLASH/FlashUniform.py:229-304: np.fft.fftn of complex128 N^3 arrays on one
+// thread, a 3*N^3 fp64 k-grid, fftshift copies and three scipy binned_statistic passes).
+//
+// Pipeline (per GPU; every array stays in FILE order [z][y][x], x fastest):
+//   K4  k_ke_weight3   w_n = sqrt(rho) * u_n for the three components in ONE pass over rho,ux,uy,uz,
+//                      written into the row-padded layout an in-place real-to-complex FFT needs.
+//   lib cuFFT          the 3-D FFT — the ONLY library call on this path (BASELINE.json north_star):
+//                      batched 2-D D2Z over (y,x) per z-plane, then strided 1-D Z2Z along z, both in
+//                      place.  Hermitian (r2c) storage: complex [kz][ky][kx = 0..N/2].
+//   K6  k_spectrum_bin |u^|^2, the reference's longitudinal projection INCLUDING its `.T` quirk
+//                      (FlashUniform.py:281: ffts[n].T reverses all axes, i.e. the operand is taken at
+//                      the transposed wavevector (kz,ky,kx)), shell index floor(|k|+1/2) in exact
+//                      integer arithmetic, per-shell sums with weight 2 for the kx>0 half.
+//       k_spectrum_reduce / fava_spectrum_finalize: fixed-order merge, shell mean x 4 pi k^2.
+//
+// Why r2c is exact for this statistic: both `total` and the quirky `longitudinal` are invariant under
+// k -> -k for a real input (u^(-k) = conj u^(k)), so the kx<0 half contributes the same values as its
+// mirror; the Nyquist planes (|k_i| = N/2) lie beyond the last bin edge N/2-1.5 and never contribute.
+// The transposed operand u^_n(kz,ky,kx) is read from the stored half directly when kz >= 0 and as
+// conj(u^_n(-kz,-ky,-kx)) otherwise; tiles are transposed through shared memory so that both the
+// direct and the transposed reads are coalesced.  Tiles entirely outside the sphere |k| <= N/2-1.5
+// (~48 % of the half-cube) are skipped before any load.
+//
+// Determinism: lanes of a warp hold consecutive kx of one (ky,kz) row, so shell indices are
+// non-decreasing along the warp; a segmented shuffle scan reduces them in a fixed order, segment
+// tails add into warp-private tile bins (plain stores), the CTA merges its warps in a fixed order,
+// CTAs own a fixed tile sequence, and k_spectrum_reduce sums CTA partials in index order.
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+
+namespace fava {
+
+// ------------------------------------------------------------------------------------------------
+// K4: weighting
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+    k_ke_weight3(const T* __restrict__ rho, const T* __restrict__ ux, const T* __restrict__ uy,
+                 const T* __restrict__ uz, int64_t nrows, int64_t nx, int64_t pitch, double* __restrict__ wx,
+                 double* __restrict__ wy, double* __restrict__ wz) {
+    // one thread = two consecutive x of one row (nx is even); grid-stride over pairs
+    const int64_t half = nx >> 1;
+    const int64_t npairs = nrows * half;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < npairs; q += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = q / half, xp = (q - row * half) * 2;
+        const int64_t in = row * nx + xp, out = row * pitch + xp;
+        double r[2], a[2], b[2], c[2];
+        VecLoad<T, 2>::ld(rho + in, r);
+        VecLoad<T, 2>::ld(ux + in, a);
+        VecLoad<T, 2>::ld(uy + in, b);
+        VecLoad<T, 2>::ld(uz + in, c);
+        const double s0 = sqrt(r[0]), s1 = sqrt(r[1]);
+        *reinterpret_cast<double2*>(wx + out) = make_double2(s0 * a[0], s1 * a[1]);
+        *reinterpret_cast<double2*>(wy + out) = make_double2(s0 * b[0], s1 * b[1]);
+        *reinterpret_cast<double2*>(wz + out) = make_double2(s0 * c[0], s1 * c[1]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6: power, projection and shell binning
+// ------------------------------------------------------------------------------------------------
+constexpr int kTS = 32;        // tile edge in kx and kz
+constexpr int kBinT = 256;     // threads per CTA (8 warps, 4 kz rows each)
+constexpr int kBinWarps = kBinT / 32;
+constexpr int kSlots = 64;     // shell span of one tile (<= 31*sqrt(2) + 2)
+
+struct BinParams {
+    int n, nxh, ny_local, nbins, kmax2, ntx, ntz;
+    int64_t ntiles;
+    int64_t zstride;  // ny_local * nxh (complex elements per kz plane)
+    const int32_t* ky_of_local;  // NULL = identity (local row jl holds global ky index jl)
+    const int32_t* local_of_ky;  // NULL = identity
+    double norm2;
+};
+
+__device__ __forceinline__ int shell_of(int k2) {
+    // m such that m^2 - m < k2 <= m^2 + m  <=>  m - 1/2 < sqrt(k2) < m + 1/2  (k2 integer: no ties)
+    int m = (int)(sqrt((double)k2) + 0.5);
+    while (m * m + m < k2) ++m;
+    while (m > 0 && m * m - m >= k2) --m;
+    return m;
+}
+
+__global__ void __launch_bounds__(kBinT)
+    k_spectrum_bin(const double2* __restrict__ fx, const double2* __restrict__ fy, const double2* __restrict__ fz,
+                   BinParams p, double* __restrict__ partial) {
+    extern __shared__ double dyn[];  // [tot nbins][lon nbins][cnt nbins]
+    double* cta_tot = dyn;
+    double* cta_lon = dyn + p.nbins;
+    double* cta_cnt = dyn + 2 * p.nbins;
+    __shared__ double2 S[kTS][kTS + 1];
+    __shared__ double wb_tot[kBinWarps][kSlots];
+    __shared__ double wb_lon[kBinWarps][kSlots];
+    __shared__ double wb_cnt[kBinWarps][kSlots];
+
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (int i = t; i < 3 * p.nbins; i += kBinT) dyn[i] = 0.0;
+    for (int i = t; i < kBinWarps * kSlots; i += kBinT) {
+        (&wb_tot[0][0])[i] = 0.0;
+        (&wb_lon[0][0])[i] = 0.0;
+        (&wb_cnt[0][0])[i] = 0.0;
+    }
+    __syncthreads();
+
+    const int n = p.n, nh = n >> 1;
+    const double2* F[3] = {fx, fy, fz};
+
+    for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        const int tx = (int)(tile % p.ntx);
+        const int tz = (int)((tile / p.ntx) % p.ntz);
+        const int jl = (int)(tile / ((int64_t)p.ntx * p.ntz));
+        const int j = p.ky_of_local ? p.ky_of_local[jl] : jl;
+        if (j == nh) continue;  // Nyquist ky plane: beyond the last bin
+        const int ky = j < nh ? j : j - n;
+        const int a0 = tx * kTS, b0 = tz * kTS;
+        const int lend = min(b0 + kTS - 1, n - 1);
+        const int f0 = b0 < nh ? b0 : n - b0, f1 = lend < nh ? lend : n - lend;
+        const int kzmin = min(f0, f1);
+        const int k2min = a0 * a0 + ky * ky + kzmin * kzmin;
+        if (k2min > p.kmax2) continue;  // tile outside the sphere (uniform for the CTA)
+        const int mlo = shell_of(k2min);
+        const int jm = (n - j) % n;
+        const int jml = p.local_of_ky ? p.local_of_ky[jm] : jm;
+
+        // this thread's points: kx = a0 + lane, kz rows b0 + warp + 8 i
+        const int kx = a0 + lane;
+        double lre[4], lim[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) lre[i] = lim[i] = 0.0;
+        double tot[4] = {0.0, 0.0, 0.0, 0.0};
+
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            // transposed operand tile: S[a][b] = u^_c at (x-wn = kz(b), y-wn = ky, z-wn = kx(a))
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int a = warp + kBinWarps * i;  // kx_local (row being loaded)
+                const int kxa = a0 + a;
+                const int l = b0 + lane;             // kz index of this lane
+                double2 v = make_double2(0.0, 0.0);
+                if (kxa < nh && l < n && l != nh) {
+                    if (l < nh) {
+                        v = F[c][(int64_t)kxa * p.zstride + (int64_t)jl * p.nxh + l];
+                    } else {
+                        const int zi = (n - kxa) % n;
+                        v = F[c][(int64_t)zi * p.zstride + (int64_t)jml * p.nxh + (n - l)];
+                        v.y = -v.y;
+                    }
+                }
+                S[a][lane] = v;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int b = warp + kBinWarps * i;  // kz_local
+                const int l = b0 + b;
+                if (kx < nh && l < n && l != nh) {
+                    const int kz = l < nh ? l : l - n;
+                    const double kc = c == 0 ? (double)kx : (c == 1 ? (double)ky : (double)kz);
+                    const double2 tv = S[lane][b];
+                    lre[i] = fma(kc, tv.x, lre[i]);
+                    lim[i] = fma(kc, tv.y, lim[i]);
+                    const double2 d = F[c][(int64_t)l * p.zstride + (int64_t)jl * p.nxh + kx];
+                    tot[i] += d.x * d.x + d.y * d.y;
+                }
+            }
+            __syncthreads();
+        }
+
+        // shell-wise warp reduction of the 4 rows
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int l = b0 + warp + kBinWarps * i;
+            int key = -1;
+            double vt = 0.0, vl = 0.0, vc = 0.0;
+            if (kx < nh && l < n && l != nh) {
+                const int kz = l < nh ? l : l - n;
+                const int k2 = kx * kx + ky * ky + kz * kz;
+                if (k2 <= p.kmax2) {
+                    key = shell_of(k2);
+                    const double w = kx == 0 ? 1.0 : 2.0;
+                    vt = w * 0.5 * tot[i] * p.norm2;
+                    vl = k2 > 0 ? w * (lre[i] * lre[i] + lim[i] * lim[i]) / (double)k2 * p.norm2 : 0.0;
+                    vc = w;
+                }
+            }
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int ko = __shfl_up_sync(0xffffffffu, key, d);
+                const double to = __shfl_up_sync(0xffffffffu, vt, d);
+                const double lo = __shfl_up_sync(0xffffffffu, vl, d);
+                const double co = __shfl_up_sync(0xffffffffu, vc, d);
+                if (lane >= d && ko == key) vt += to, vl += lo, vc += co;
+            }
+            const int kn = __shfl_down_sync(0xffffffffu, key, 1);
+            const bool tail = (lane == 31) || (kn != key);
+            if (tail && key >= 0) {
+                const int s = min(key - mlo, kSlots - 1);
+                wb_tot[warp][s] += vt;
+                wb_lon[warp][s] += vl;
+                wb_cnt[warp][s] += vc;
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        if (t < kSlots) {
+            double st = 0.0, sl = 0.0, sc = 0.0;
+#pragma unroll
+            for (int w = 0; w < kBinWarps; ++w) {
+                st += wb_tot[w][t], sl += wb_lon[w][t], sc += wb_cnt[w][t];
+                wb_tot[w][t] = 0.0, wb_lon[w][t] = 0.0, wb_cnt[w][t] = 0.0;
+            }
+            const int m = mlo + t;
+            if (m < p.nbins && sc != 0.0) cta_tot[m] += st, cta_lon[m] += sl, cta_cnt[m] += sc;
+        }
+        __syncthreads();
+    }
+    double* out = partial + (int64_t)blockIdx.x * 3 * p.nbins;
+    for (int i = t; i < 3 * p.nbins; i += kBinT) out[i] = dyn[i];
+}
+
+__global__ void k_spectrum_reduce(const double* __restrict__ partial, int ncta, int nvals, double* __restrict__ sums) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nvals) return;
+    double s = 0.0;
+    for (int c = 0; c < ncta; ++c) s += partial[(int64_t)c * nvals + i];
+    sums[i] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// cuFFT plans (cached in the context; one shared work area)
+// ------------------------------------------------------------------------------------------------
+enum PlanKind { PLAN_XY = 1, PLAN_Z = 2 };
+
+static int get_plan(fava_ctx* ctx, int kind, int64_t a, int64_t b, int64_t c, cufftHandle* out) {
+    const auto key = std::make_tuple(kind, a, b, c);
+    auto it = ctx->plans.find(key);
+    if (it != ctx->plans.end()) {
+        *out = it->second;
+        return FAVA_OK;
+    }
+    cufftHandle h;
+    FAVA_CHECK_CUFFT(cufftCreate(&h));
+    FAVA_CHECK_CUFFT(cufftSetAutoAllocation(h, 0));
+    size_t work = 0;
+    cufftResult r;
+    if (kind == PLAN_XY) {  // a = batch (planes), b = ny, c = nx : in-place 2-D D2Z over padded rows
+        long long dims[2] = {(long long)b, (long long)c};
+        long long nxh = c / 2 + 1;
+        long long inembed[2] = {(long long)b, 2 * nxh};
+        long long onembed[2] = {(long long)b, nxh};
+        r = cufftMakePlanMany64(h, 2, dims, inembed, 1, (long long)b * 2 * nxh, onembed, 1, (long long)b * nxh,
+                                CUFFT_D2Z, (long long)a, &work);
+    } else {  // a = nz (transform length), b = rows (stride and batch) : in-place strided 1-D Z2Z
+        long long dims[1] = {(long long)a};
+        long long embed[1] = {(long long)a};
+        r = cufftMakePlanMany64(h, 1, dims, embed, (long long)b, 1, embed, (long long)b, 1, CUFFT_Z2Z, (long long)b,
+                                &work);
+    }
+    if (r != CUFFT_SUCCESS) {
+        cufftDestroy(h);
+        return set_error(FAVA_ECUDA, "cufftMakePlanMany64(kind %d, %lld, %lld, %lld) failed: cufftResult %d", kind,
+                         (long long)a, (long long)b, (long long)c, (int)r);
+    }
+    ctx->plans[key] = h;
+    ctx->plan_work[key] = work;
+    *out = h;
+    return FAVA_OK;
+}
+
+static int exec_plan(fava_ctx* ctx, int kind, int64_t a, int64_t b, int64_t c, double* data, cudaStream_t st) {
+    cufftHandle h = 0;
+    int rc = get_plan(ctx, kind, a, b, c, &h);
+    if (rc) return rc;
+    const size_t work = ctx->plan_work[std::make_tuple(kind, a, b, c)];
+    void* ws = nullptr;
+    if (work) {
+        rc = ctx_workspace(ctx, WS_FFT0, work, &ws);
+        if (rc) return rc;
+    }
+    FAVA_CHECK_CUFFT(cufftSetWorkArea(h, ws));
+    FAVA_CHECK_CUFFT(cufftSetStream(h, st));
+    if (kind == PLAN_XY) FAVA_CHECK_CUFFT(cufftExecD2Z(h, (cufftDoubleReal*)data, (cufftDoubleComplex*)data));
+    else FAVA_CHECK_CUFFT(cufftExecZ2Z(h, (cufftDoubleComplex*)data, (cufftDoubleComplex*)data, CUFFT_FORWARD));
+    g_launches.fetch_add(1, std::memory_order_relaxed);  // counted once per library call (cuFFT may launch several)
+    return FAVA_OK;
+}
+
+static int check_cube(int64_t n, const char* who) {
+    if (n < 4 || (n & 1)) return set_error(FAVA_EINVAL, "%s: grid size %lld must be even and >= 4 (the reference's "
+                                           "k-grid is integer only for even N, FlashUniform.py:244-253)", who, (long long)n);
+    if (n > 4096) return set_error(FAVA_EINVAL, "%s: grid size %lld too large", who, (long long)n);
+    return FAVA_OK;
+}
+
+}  // namespace fava
+
+using namespace fava;
+
+extern "C" {
+
+int fava_ke_weight3(fava_ctx* ctx, const void* d_rho, const void* d_ux, const void* d_uy, const void* d_uz, int dtype,
+                    int64_t nrows, int64_t nx, int64_t pitch, double* d_wx, double* d_wy, double* d_wz, void* stream) {
+    FAVA_REQUIRE(ctx && d_rho && d_ux && d_uy && d_uz && d_wx && d_wy && d_wz, "fava_ke_weight3: NULL argument");
+    FAVA_REQUIRE(nrows > 0 && nx > 0 && (nx & 1) == 0, "fava_ke_weight3: need nrows > 0 and an even nx");
+    FAVA_REQUIRE(pitch >= nx && (pitch & 1) == 0, "fava_ke_weight3: pitch must be even and >= nx");
+    FAVA_REQUIRE(dtype == FAVA_F32 || dtype == FAVA_F64, "fava_ke_weight3: bad dtype %d", dtype);
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t npairs = nrows * (nx / 2);
+    const unsigned grid = (unsigned)std::min<int64_t>((npairs + 255) / 256, (int64_t)ctx->num_sms * 32);
+    if (dtype == FAVA_F64)
+        k_ke_weight3<double><<<grid, 256, 0, st>>>((const double*)d_rho, (const double*)d_ux, (const double*)d_uy,
+                                                   (const double*)d_uz, nrows, nx, pitch, d_wx, d_wy, d_wz);
+    else
+        k_ke_weight3<float><<<grid, 256, 0, st>>>((const float*)d_rho, (const float*)d_ux, (const float*)d_uy,
+                                                  (const float*)d_uz, nrows, nx, pitch, d_wx, d_wy, d_wz);
+    FAVA_LAUNCHED();
+    return FAVA_OK;
+}
+
+int fava_fft_xy(fava_ctx* ctx, double* d_data, int64_t nz_local, int64_t ny, int64_t nx, void* stream) {
+    FAVA_REQUIRE(ctx && d_data, "fava_fft_xy: NULL argument");
+    FAVA_REQUIRE(nz_local > 0 && ny > 0 && nx > 1 && (nx & 1) == 0, "fava_fft_xy: bad shape");
+    DeviceGuard g(ctx->device);
+    return exec_plan(ctx, PLAN_XY, nz_local, ny, nx, d_data, (cudaStream_t)stream);
+}
+
+int fava_fft_z(fava_ctx* ctx, double* d_data, int64_t nz, int64_t rows, void* stream) {
+    FAVA_REQUIRE(ctx && d_data, "fava_fft_z: NULL argument");
+    FAVA_REQUIRE(nz > 0 && rows > 0, "fava_fft_z: bad shape");
+    DeviceGuard g(ctx->device);
+    return exec_plan(ctx, PLAN_Z, nz, rows, 0, d_data, (cudaStream_t)stream);
+}
+
+int fava_spectrum_bin(fava_ctx* ctx, const double* d_fx, const double* d_fy, const double* d_fz, int64_t n,
+                      int64_t ny_local, const int32_t* d_ky_of_local, const int32_t* d_local_of_ky, double norm,
+                      double* d_sums, void* stream) {
+    FAVA_REQUIRE(ctx && d_fx && d_fy && d_fz && d_sums, "fava_spectrum_bin: NULL argument");
+    int rc = check_cube(n, "fava_spectrum_bin");
+    if (rc) return rc;
+    FAVA_REQUIRE(ny_local > 0 && ny_local <= n, "fava_spectrum_bin: ny_local %lld not in 1..%lld", (long long)ny_local,
+                 (long long)n);
+    FAVA_REQUIRE((d_ky_of_local == nullptr) == (d_local_of_ky == nullptr),
+                 "fava_spectrum_bin: pass both ky maps or neither");
+    FAVA_REQUIRE(d_ky_of_local || ny_local == n, "fava_spectrum_bin: a partial ky range needs the ky maps");
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    BinParams p;
+    p.n = (int)n, p.nxh = (int)(n / 2 + 1), p.ny_local = (int)ny_local;
+    p.nbins = (int)(n / 2 - 1);
+    p.kmax2 = (int)(n * n / 4 - 3 * n / 2 + 2);
+    p.ntx = (int)((n / 2 + kTS - 1) / kTS);
+    p.ntz = (int)((n + kTS - 1) / kTS);
+    p.ntiles = (int64_t)p.ntx * p.ntz * ny_local;
+    p.zstride = ny_local * (int64_t)p.nxh;
+    p.ky_of_local = d_ky_of_local, p.local_of_ky = d_local_of_ky;
+    p.norm2 = norm * norm;
+    const size_t dyn = sizeof(double) * 3 * (size_t)p.nbins;
+    const int ncta = (int)std::min<int64_t>(p.ntiles, (int64_t)ctx->num_sms * 4);
+    void* ws;
+    rc = ctx_workspace(ctx, WS_PARTIALS, sizeof(double) * 3 * (size_t)p.nbins * ncta, &ws);
+    if (rc) return rc;
+    if (dyn > 16 * 1024)
+        FAVA_CHECK_CUDA(cudaFuncSetAttribute(k_spectrum_bin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    k_spectrum_bin<<<ncta, kBinT, dyn, st>>>((const double2*)d_fx, (const double2*)d_fy, (const double2*)d_fz, p,
+                                            (double*)ws);
+    FAVA_LAUNCHED();
+    const int nvals = 3 * p.nbins;
+    k_spectrum_reduce<<<(nvals + 127) / 128, 128, 0, st>>>((const double*)ws, ncta, nvals, d_sums);
+    FAVA_LAUNCHED();
+    return FAVA_OK;
+}
+
+int fava_spectrum_finalize(fava_ctx* ctx, const double* d_sums, int64_t n, double* h_k, double* h_total,
+                           double* h_long, double* h_trans, void* stream) {
+    FAVA_REQUIRE(ctx && d_sums && h_k && h_total && h_long && h_trans, "fava_spectrum_finalize: NULL argument");
+    int rc = check_cube(n, "fava_spectrum_finalize");
+    if (rc) return rc;
+    DeviceGuard g(ctx->device);
+    const int nb = (int)(n / 2 - 1);
+    std::vector<double> h((size_t)3 * nb);
+    FAVA_CHECK_CUDA(cudaMemcpyAsync(h.data(), d_sums, sizeof(double) * 3 * nb, cudaMemcpyDeviceToHost,
+                                    (cudaStream_t)stream));
+    FAVA_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    const double two_pi_dm1 = 2.0 * M_PI * 2.0;  // 2 pi (ndim - 1), ndim = 3 (FlashUniform.py:295-297)
+    for (int m = 0; m < nb; ++m) {
+        const double k = (double)m;  // bin_edges[:-1] + 0.5 (FlashUniform.py:291)
+        const double cnt = h[2 * nb + m];
+        const double factor = k * k * two_pi_dm1;
+        const double mt = h[m] / cnt, ml = h[nb + m] / cnt;  // 0/0 -> NaN like an empty scipy bin
+        h_k[m] = k;
+        h_total[m] = mt * factor;
+        h_long[m] = ml * factor;
+        h_trans[m] = (mt - ml) * factor;
+    }
+    return FAVA_OK;
+}
+
+int fava_ke_spectrum(fava_ctx* ctx, const void* d_rho, const void* d_ux, const void* d_uy, const void* d_uz,
+                     int dtype, int64_t n, double* h_k, double* h_total, double* h_long, double* h_trans,
+                     void* stream) {
+    FAVA_REQUIRE(ctx && d_rho && d_ux && d_uy && d_uz, "fava_ke_spectrum: NULL argument");
+    int rc = check_cube(n, "fava_ke_spectrum");
+    if (rc) return rc;
+    DeviceGuard g(ctx->device);
+    const int64_t nxh = n / 2 + 1;
+    const size_t comp_bytes = sizeof(double) * 2 * (size_t)(n * n * nxh);
+    void* w[3];
+    for (int c = 0; c < 3; ++c) {
+        rc = ctx_workspace(ctx, WS_FFT1 + c, comp_bytes, &w[c]);
+        if (rc) return rc;
+    }
+    void* sums;
+    rc = ctx_workspace(ctx, WS_AUX, sizeof(double) * 3 * (size_t)(n / 2 - 1), &sums);
+    if (rc) return rc;
+    rc = fava_ke_weight3(ctx, d_rho, d_ux, d_uy, d_uz, dtype, n * n, n, 2 * nxh, (double*)w[0], (double*)w[1],
+                         (double*)w[2], stream);
+    if (rc) return rc;
+    for (int c = 0; c < 3; ++c) {
+        rc = fava_fft_xy(ctx, (double*)w[c], n, n, n, stream);
+        if (rc) return rc;
+        rc = fava_fft_z(ctx, (double*)w[c], n, n * nxh, stream);
+        if (rc) return rc;
+    }
+    const double norm = 1.0 / ((double)n * (double)n * (double)n);  // norm="forward" (FlashUniform.py:268)
+    rc = fava_spectrum_bin(ctx, (const double*)w[0], (const double*)w[1], (const double*)w[2], n, n, nullptr, nullptr,
+                           norm, (double*)sums, stream);
+    if (rc) return rc;
+    return fava_spectrum_finalize(ctx, (const double*)sums, n, h_k, h_total, h_long, h_trans, stream);
+}
+
+}  // extern "C"

@@ -171,3 +171,159 @@ def plane_profiles(rho, ux, uy, uz, axis: int, cell_volume: float, layer_volume:
 
 def to_host(t: torch.Tensor) -> np.ndarray:
     return t.detach().cpu().numpy()
+
+
+# ---- block-list front end (AMR / multi-block files) ------------------------------------------------
+def _check_blocks(rho, ux, uy, uz) -> tuple[int, int, int, int]:
+    if rho.dim() != 4:
+        raise ValueError(f"expected a [block][z][y][x] array, got shape {tuple(rho.shape)}")
+    for t in (rho, ux, uy, uz):
+        if not t.is_cuda:
+            raise ValueError("fields must be CUDA tensors (no CPU fallback)")
+        if t.shape != rho.shape or t.dtype != rho.dtype or t.device != rho.device:
+            raise ValueError("rho, ux, uy, uz must share shape, dtype and device")
+        if not t.is_contiguous():
+            raise ValueError("fields must be contiguous in [block][z][y][x] order")
+    nb, nzb, nyb, nxb = (int(s) for s in rho.shape)
+    return nb, nzb, nyb, nxb
+
+
+LEAF_DTYPE = np.dtype([("block", "<i8"), ("ilo", "<i8"), ("scale", "<i4"), ("pad_", "<i4"), ("vol_frac", "<f8")])
+PROLONG_DTYPE = np.dtype([("block", "<i8"), ("off", "<i4", (3,)), ("scale", "<i4")])
+
+
+class HostTable:
+    """A host array of C structs (numpy structured array) plus its ctypes pointer."""
+
+    def __init__(self, arr: np.ndarray, ctype):
+        self.arr = np.ascontiguousarray(arr)
+        self.n = int(arr.shape[0])
+        self.ptr = C.cast(C.c_void_p(self.arr.ctypes.data if self.n else 0), C.POINTER(ctype))
+
+
+def leaf_table(blocks, ilo, scale, vol_frac) -> HostTable:
+    """fava_leaf_desc[] from host sequences (block index, first bin, lref_n, vol_frac)."""
+    arr = np.zeros(len(blocks), dtype=LEAF_DTYPE)
+    arr["block"], arr["ilo"], arr["scale"], arr["vol_frac"] = blocks, ilo, scale, vol_frac
+    return HostTable(arr, _lib.LeafDesc)
+
+
+def plane_moments_blocks(rho, ux, uy, uz, axis: int, table: HostTable, nbins: int):
+    """Pivoted plane moments of the leaves in `table` -> (moments [14][nbins], pivots [3][nbins]),
+    already weighted by vol_frac (fava_plane_moments_blocks)."""
+    nb, nzb, nyb, nxb = _check_blocks(rho, ux, uy, uz)
+    if axis not in (0, 1, 2):
+        raise ValueError(f"Do not recognize AXIS enumeration {axis}")
+    ctx = get_context(rho.device)
+    mom = torch.empty((FAVA_NMOM, nbins), dtype=torch.float64, device=rho.device)
+    piv = torch.empty((3, nbins), dtype=torch.float64, device=rho.device)
+    _lib.check(
+        ctx.lib.fava_plane_moments_blocks(ctx.handle, _ptr(rho), _ptr(ux), _ptr(uy), _ptr(uz), _dtype_code(rho), nzb,
+                                          nyb, nxb, int(axis), table.ptr, table.n, int(nbins), _ptr(mom), _ptr(piv),
+                                          _stream(rho)),
+        "fava_plane_moments_blocks",
+    )
+    return mom, piv
+
+
+def plane_sum(field: torch.Tensor, axis: int) -> torch.Tensor:
+    """Plane sums [nbins] of one dense [z][y][x] field (fava_plane_sum)."""
+    nz, ny, nx = _check_fields(field, field, field, field)
+    if axis not in (0, 1, 2):
+        raise ValueError(f"Do not recognize AXIS enumeration {axis}")
+    ctx = get_context(field.device)
+    out = torch.empty((nx, ny, nz)[axis], dtype=torch.float64, device=field.device)
+    _lib.check(ctx.lib.fava_plane_sum(ctx.handle, _ptr(field), _dtype_code(field), nz, ny, nx, int(axis), _ptr(out),
+                                      _stream(field)), "fava_plane_sum")
+    return out
+
+
+def plane_sum_blocks(blocks: torch.Tensor, axis: int, table: HostTable, nbins: int) -> torch.Tensor:
+    """vol_frac-weighted plane sums of the table's leaves scattered to the fine bins (fava_plane_sum_blocks)."""
+    nb, nzb, nyb, nxb = _check_blocks(blocks, blocks, blocks, blocks)
+    if axis not in (0, 1, 2):
+        raise ValueError(f"Do not recognize AXIS enumeration {axis}")
+    ctx = get_context(blocks.device)
+    out = torch.empty(nbins, dtype=torch.float64, device=blocks.device)
+    _lib.check(ctx.lib.fava_plane_sum_blocks(ctx.handle, _ptr(blocks), _dtype_code(blocks), nzb, nyb, nxb, int(axis),
+                                             table.ptr, table.n, int(nbins), _ptr(out), _stream(blocks)),
+               "fava_plane_sum_blocks")
+    return out
+
+
+# ---- prolongation ------------------------------------------------------------------------------------
+def prolong_table(blocks, offs_xyz, scale) -> HostTable:
+    """fava_prolong_leaf[] (source block, fine-cell corner relative to the output, 2^(L-level))."""
+    arr = np.zeros(len(blocks), dtype=PROLONG_DTYPE)
+    arr["block"], arr["scale"] = blocks, scale
+    if len(blocks):
+        arr["off"] = np.asarray(offs_xyz, dtype=np.int32).reshape(-1, 3)
+    return HostTable(arr, _lib.ProlongLeaf)
+
+
+def prolong(blocks: torch.Tensor, table: HostTable, out_zyx: tuple[int, int, int],
+            out: torch.Tensor | None = None) -> torch.Tensor:
+    """Piecewise-constant injection of the table's leaves into a uniform fp64 [NZ][NY][NX] array."""
+    if blocks.dim() != 4 or not blocks.is_cuda or not blocks.is_contiguous():
+        raise ValueError("blocks must be a contiguous CUDA tensor [block][z][y][x]")
+    _, nzb, nyb, nxb = (int(s) for s in blocks.shape)
+    NZ, NY, NX = (int(v) for v in out_zyx)
+    ctx = get_context(blocks.device)
+    if out is None:
+        out = torch.empty((NZ, NY, NX), dtype=torch.float64, device=blocks.device)
+    _lib.check(
+        ctx.lib.fava_prolong(ctx.handle, _ptr(blocks), _dtype_code(blocks), nzb, nyb, nxb, table.ptr, table.n, NZ, NY,
+                             NX, _ptr(out), _stream(blocks)),
+        "fava_prolong",
+    )
+    return out
+
+
+# ---- kinetic-energy spectrum ---------------------------------------------------------------------------
+SPECTRUM_KEYS = ("k", "total", "longitudinal", "transverse")
+
+
+def ke_spectrum(rho, ux, uy, uz) -> dict[str, np.ndarray]:
+    """Whole single-GPU pipeline (fava_ke_spectrum) for a cubic [N][N][N] grid -> the reference's dict."""
+    nz, ny, nx = _check_fields(rho, ux, uy, uz)
+    if not (nz == ny == nx):
+        raise ValueError(f"kinetic_energy_spectra needs a cubic grid (the reference's `.T` projection, "
+                         f"FlashUniform.py:281, fails otherwise); got {(nx, ny, nz)}")
+    n = nx
+    ctx = get_context(rho.device)
+    nb = n // 2 - 1
+    bufs = [np.empty(max(nb, 0), dtype=np.float64) for _ in range(4)]
+    ptrs = [b.ctypes.data_as(_lib.c_double_p) for b in bufs]
+    _lib.check(
+        ctx.lib.fava_ke_spectrum(ctx.handle, _ptr(rho), _ptr(ux), _ptr(uy), _ptr(uz), _dtype_code(rho), n, *ptrs,
+                                 _stream(rho)),
+        "fava_ke_spectrum",
+    )
+    return dict(zip(SPECTRUM_KEYS, bufs))
+
+
+# ---- staging ---------------------------------------------------------------------------------------------
+def stage_file(path, file_offset: int, nbytes: int, out: torch.Tensor) -> torch.Tensor:
+    """pread `nbytes` at `file_offset` of `path` through the pinned ring into `out` (async on the current stream)."""
+    if not out.is_cuda or not out.is_contiguous() or out.numel() * out.element_size() < nbytes:
+        raise ValueError("stage_file: `out` must be a contiguous CUDA tensor of at least nbytes")
+    ctx = get_context(out.device)
+    _lib.check(
+        ctx.lib.fava_stage_h2d(ctx.handle, str(path).encode(), int(file_offset), int(nbytes), _ptr(out), _stream(out)),
+        "fava_stage_h2d",
+    )
+    return out
+
+
+def stage_host(arr: np.ndarray, out: torch.Tensor) -> torch.Tensor:
+    """Host ndarray (pageable or pinned, C-contiguous) -> device tensor through the pinned ring."""
+    if not arr.flags.c_contiguous:
+        raise ValueError("stage_host: array must be C-contiguous")
+    if not out.is_cuda or not out.is_contiguous() or out.numel() * out.element_size() != arr.nbytes:
+        raise ValueError("stage_host: `out` must be a contiguous CUDA tensor of the same byte size")
+    ctx = get_context(out.device)
+    _lib.check(
+        ctx.lib.fava_stage_host_h2d(ctx.handle, C.c_void_p(arr.ctypes.data), int(arr.nbytes), _ptr(out), _stream(out)),
+        "fava_stage_host_h2d",
+    )
+    return out

@@ -93,3 +93,30 @@ def all_gather_cat(t: torch.Tensor, dim: int = 0) -> torch.Tensor:
 def barrier() -> None:
     if world_size() > 1:
         dist.barrier()
+
+
+def gather_cat_to_root(t: torch.Tensor) -> torch.Tensor | None:
+    """Concatenate per-rank tensors along dim 0 on rank 0 (parts may differ in length); None elsewhere."""
+    if world_size() == 1:
+        return t
+    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    counts = [torch.zeros_like(n) for _ in range(world_size())]
+    dist.all_gather(counts, n)
+    counts = [int(c.item()) for c in counts]
+    if is_root():
+        parts = [torch.empty((c,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device) for c in counts]
+        parts[0] = t
+        for r in range(1, world_size()):
+            dist.recv(parts[r], src=r)
+        return torch.cat(parts, dim=0)
+    dist.send(t.contiguous(), dst=0)
+    return None
+
+
+def all_gather_rows(t: torch.Tensor) -> list[torch.Tensor]:
+    """All ranks' equally-shaped tensors, in rank order."""
+    if world_size() == 1:
+        return [t]
+    parts = [torch.empty_like(t) for _ in range(world_size())]
+    dist.all_gather(parts, t.contiguous())
+    return parts

@@ -31,3 +31,47 @@ def slab_profiles(rho, ux, uy, uz, axis: int, cell_volume: float, layer_volume: 
     if gather and dist.world_size() > 1:
         out = {k: dist.all_gather_cat(v, dim=1) for k, v in out.items()}
     return out
+
+
+def agree_pivots(mom: torch.Tensor, piv: torch.Tensor) -> torch.Tensor:
+    """Block-range ranks pick their pivots from their own first block plane per bin; before the
+    moments can be summed across ranks they must refer to ONE pivot per bin.  Every rank adopts the
+    pivot of the lowest rank that actually holds data for the bin (weight row > 0) and re-expresses
+    its moments about it (exact algebra, fava_moments_repivot)."""
+    if dist.world_size() == 1:
+        return piv
+    has = (mom[13] > 0).to(torch.float64)
+    packed = torch.cat([piv, has[None, :]], dim=0)
+    allp = dist.all_gather_rows(packed)
+    common = torch.zeros_like(piv)
+    chosen = torch.zeros_like(has)
+    for part in allp:  # rank order
+        take = (chosen == 0) & (part[3] > 0)
+        common = torch.where(take[None, :], part[:3], common)
+        chosen = torch.where(take, torch.ones_like(chosen), chosen)
+    device.moments_repivot(mom, piv, common)
+    return common
+
+
+def block_profiles(rho, ux, uy, uz, axis: int, table, nbins: int, layer_volume: float,
+                   favre: bool = True) -> dict[str, torch.Tensor]:
+    """Profiles of a block dataset whose leaves are sharded over ranks as contiguous block ranges
+    (the reference's MPI decomposition, _flash.py:166-208, :803-822)."""
+    mom, piv = device.plane_moments_blocks(rho, ux, uy, uz, axis, table, nbins)
+    if dist.world_size() > 1:
+        piv = agree_pivots(mom, piv)
+        dist.allreduce_sum_(mom)
+    return device.moments_finalize(mom, piv, 1.0, layer_volume, favre=favre)
+
+
+def slab_plane_sum(field, axis: int, cell_volume: float) -> torch.Tensor:
+    """vf-weighted plane integral of one field held as z-slabs (reference slice_integral, _flash.py:1451-1504)."""
+    out = device.plane_sum(field, axis) * cell_volume
+    if axis in (0, 1):
+        return dist.allreduce_sum_(out)
+    return dist.all_gather_cat(out, dim=0)
+
+
+def block_plane_sum(blocks, axis: int, table, nbins: int) -> torch.Tensor:
+    out = device.plane_sum_blocks(blocks, axis, table, nbins)
+    return dist.allreduce_sum_(out)

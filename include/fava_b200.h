@@ -127,6 +127,11 @@ int fava_moments_finalize(fava_ctx* ctx, const double* d_moments, const double* 
  * _flash.py:1451-1504).  Dense array; d_out [nbins] = sum over plane (unweighted). */
 int fava_plane_sum(fava_ctx* ctx, const void* d_field, int dtype, int64_t nz, int64_t ny, int64_t nx,
                    int axis, double* d_out, void* stream);
+/* Block-list variant: d_out [nbins] = sum over leaves of vol_frac * plane sums, scattered to the fine
+ * bins like fava_plane_moments_blocks (_flash.py:1488-1498). */
+int fava_plane_sum_blocks(fava_ctx* ctx, const void* d_field, int dtype, int64_t nzb, int64_t nyb, int64_t nxb,
+                          int axis, const fava_leaf_desc* h_leaves, int64_t nleaf, int64_t nbins, double* d_out,
+                          void* stream);
 
 /* ---- AMR -> uniform prolongation (reference: FLASH.from_amr gather, _flash.py:1262-1321) ----- */
 
@@ -156,30 +161,36 @@ int fava_ke_spectrum(fava_ctx* ctx, const void* d_rho, const void* d_ux, const v
 
 /* Building blocks of the same pipeline, exposed for the slab-decomposed (multi-GPU) driver. */
 
-/* w[n] = sqrt(rho) * u for one slab of nz_local planes; d_w real fp64 [nz_local][ny][nx]. */
-int fava_ke_weight(fava_ctx* ctx, const void* d_rho, const void* d_u, int dtype, int64_t ncells,
-                   double* d_w, void* stream);
-/* Batched FFTs of a slab: r2c along x then c2c along y for nz_local planes.
- * in: real [nz_local][ny][nx]; out: complex [nz_local][ny][nx/2+1] (interleaved re,im). */
-int fava_fft_xy(fava_ctx* ctx, const double* d_in, double* d_out, int64_t nz_local, int64_t ny,
-                int64_t nx, void* stream);
-/* In-place c2c FFTs along the slowest axis of complex [nz][rows] (rows = ny_local*(nx/2+1)). */
+/* w_n = sqrt(rho) * u_n for n = x,y,z in one pass (FlashUniform.py:266-268).  Inputs are `nrows` rows of
+ * `nx` cells (a z-slab: nrows = nz_local*ny); outputs are real fp64 rows of `pitch` doubles
+ * (pitch = 2*(nx/2+1): the padding an in-place real-to-complex transform needs). */
+int fava_ke_weight3(fava_ctx* ctx, const void* d_rho, const void* d_ux, const void* d_uy, const void* d_uz,
+                    int dtype, int64_t nrows, int64_t nx, int64_t pitch, double* d_wx, double* d_wy,
+                    double* d_wz, void* stream);
+/* In-place batched 2-D FFT (cuFFT D2Z) of a slab: real [nz_local][ny][2*(nx/2+1)] (padded rows) ->
+ * complex [nz_local][ny][nx/2+1] (interleaved re,im), transformed along x (halved) and y. */
+int fava_fft_xy(fava_ctx* ctx, double* d_data, int64_t nz_local, int64_t ny, int64_t nx, void* stream);
+/* In-place c2c FFTs (cuFFT Z2Z) along the slowest axis of complex [nz][rows] (rows = ny_local*(nx/2+1)). */
 int fava_fft_z(fava_ctx* ctx, double* d_data, int64_t nz, int64_t rows, void* stream);
-/* Slab -> pencil pack for the all-to-all: splits complex [nz_local][ny][nxh] by destination rank
- * along y into `nranks` contiguous send blocks [rank][nz_local][ny/nranks][nxh].  If d_peer_recv
- * is non-NULL it holds `nranks` device pointers (peer-mapped receive buffers) and block r is
- * written straight to d_peer_recv[r] + my_rank*block_elems (the exchange fused into the pack). */
-int fava_a2a_pack(fava_ctx* ctx, const double* d_in, double* d_send, double* const* d_peer_recv,
-                  int my_rank, int nranks, int64_t nz_local, int64_t ny, int64_t nxh, void* stream);
-/* Shell binning of one spectral sub-volume complex [nz][ny_local][nxh] x 3 components, holding
- * ky indices [ky0, ky0+ny_local) of an N^3 transform normalised by `norm` (1/N^3).
- * d_sums: [3][nbins] (total, longitudinal, count) partial sums, overwritten. */
-int fava_spectrum_bin(fava_ctx* ctx, const double* d_fx, const double* d_fy, const double* d_fz,
-                      int64_t n, int64_t ky0, int64_t ny_local, double norm, double* d_sums,
-                      void* stream);
-/* Shell sums -> spectra (host outputs, nbins = n/2-1 each). */
-int fava_spectrum_finalize(fava_ctx* ctx, const double* d_sums, int64_t n, double* h_k,
-                           double* h_total, double* h_long, double* h_trans, void* stream);
+/* Slab -> ky-pencil exchange, fused with the pack: rank `my_rank` holds complex [nz_local][n][nxh] after
+ * fava_fft_xy; spectral space is distributed over ky in +-ky symmetric sets (so the transposed operand of
+ * the longitudinal projection stays rank-local).  For every destination rank r the kernel gathers the ky
+ * rows owned by r (d_ky_of_dest: [nranks][nyl] global ky indices, -1 = padding) and writes them straight
+ * into r's receive buffer d_peer_recv[r] (peer-mapped device memory, or the local buffer when r ==
+ * my_rank) at [my_rank*nz_local + z][row][kx] of a complex [n][nyl][nxh] array: no staging copy, the
+ * NVLink stores overlap the gather. */
+int fava_a2a_pack(fava_ctx* ctx, const double* d_in, double* const* d_peer_recv, const int32_t* d_ky_of_dest,
+                  int my_rank, int nranks, int64_t nz_local, int64_t n, int64_t nyl, void* stream);
+/* Shell binning of one spectral sub-volume complex [n (kz)][ny_local][n/2+1] x 3 components of an n^3
+ * transform scaled by `norm` (1/n^3, norm="forward").  Row jl holds global ky index d_ky_of_local[jl];
+ * d_local_of_ky[n] is the inverse (-1 = not held); both NULL = this GPU holds every ky in order.
+ * d_sums: [3][n/2-1] = weighted sums of total, longitudinal, and the point counts (FlashUniform.py:273-293). */
+int fava_spectrum_bin(fava_ctx* ctx, const double* d_fx, const double* d_fy, const double* d_fz, int64_t n,
+                      int64_t ny_local, const int32_t* d_ky_of_local, const int32_t* d_local_of_ky, double norm,
+                      double* d_sums, void* stream);
+/* Shell sums -> spectra (host outputs, nbins = n/2-1 each): mean x 4 pi k^2 (FlashUniform.py:286-302). */
+int fava_spectrum_finalize(fava_ctx* ctx, const double* d_sums, int64_t n, double* h_k, double* h_total,
+                           double* h_long, double* h_trans, void* stream);
 
 /* ---- HDF5 block staging (reference: _read_variable_data, _flash.py:306-341) ----------------- */
 

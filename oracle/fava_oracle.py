@@ -437,3 +437,38 @@ def from_amr_gather(geom: MeshGeom, plan: AmrPlan, field: np.ndarray) -> np.ndar
         if not empty:
             out[tuple(dst)] = blk[tuple(src)]
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# next-row: FLASH.slice_integral / slice_average (_flash.py:1427-1504)
+# ------------------------------------------------------------------------------------------------
+def slice_integral(geom: MeshGeom, field: np.ndarray, axis: int = 0):
+    """Restatement of _flash.py:1451-1504 for field = float64[blk,i,j,k]; as in `reynolds_stress` the
+    plane of constant index along `axis` is reduced (the reference always reduces array axes (1,2))."""
+    ndim = geom.ndim
+    lrefcells = 2 ** (geom.refine_level_max - 1)
+    dims = [int(nb * bl * lrefcells) for nb, bl in zip(geom.nCellsVec[:ndim], geom.nBlksVec[:ndim])]
+    min_delta = geom.min_delta(axis)
+    db = geom.domain_bounds
+    nrb = int(geom.nCellsVec[axis])
+    span = np.linspace(db[axis, 0], db[axis, 1], dims[axis] + 1, dtype=np.float64)  # :1479
+    blocklist = geom.leaf_blocks()
+    alp = np.zeros(dims[axis], dtype=np.float64)
+    cell_vols = np.array([geom.cell_volume_from_level(geom.refine_level[b]) for b in blocklist], dtype=np.float64)
+    vol_fracs = cell_vols * (min_delta / geom.delta_from_level(axis, geom.refine_level[blocklist]))  # :1483-1486
+    for lb, blk in enumerate(blocklist):  # :1488-1498
+        lref_n = int(2 ** (geom.refine_level_max - 1) / 2 ** (geom.refine_level[blk] - 1))
+        ilo = int(np.argmin(np.abs(span[:-1] - geom.block_bounds[blk, axis, 0])))
+        mean = np.einsum("ijk->i", np.moveaxis(field[blk, ...], axis, 0)) * vol_fracs[lb]
+        for i in range(nrb):
+            alp[ilo + i * lref_n : ilo + (i + 1) * lref_n] += mean[i]
+    return span, alp
+
+
+def slice_average(geom: MeshGeom, field: np.ndarray, axis: int = 0):
+    """_flash.py:1427-1449: slice_integral / (min_delta * cross-section)."""
+    db = geom.domain_bounds
+    others = [a for a in range(3) if a != axis]
+    layer = (db[others[0], 1] - db[others[0], 0]) * (db[others[1], 1] - db[others[1], 0])
+    span, alp = slice_integral(geom, field, axis)
+    return span, alp / (geom.min_delta(axis) * layer)
