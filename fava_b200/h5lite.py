@@ -304,19 +304,18 @@ class Dataset:
             return np.frombuffer(bytes(a), dtype=self.dtype, count=self.size).reshape(self.shape).copy()
         if kind == "chunked":
             raise H5LiteError(f"dataset {self.name!r} is chunked; h5lite reads contiguous/compact layouts only")
-        out = np.empty(self.shape, dtype=self.dtype)
-        if a == UNDEF or out.nbytes == 0:
-            out[...] = np.zeros((), dtype=self.dtype)
-            return out
-        off, n = self.extent()
-        view = memoryview(out).cast("B") if out.flags.c_contiguous else None
-        done = 0
-        while done < n:
-            got = os.preadv(self._r.fd, [view[done : min(n, done + (1 << 30))]], off + done)
-            if got <= 0:
-                raise H5LiteError(f"short read in dataset {self.name!r}")
-            done += got
-        return out
+        n = self.nbytes
+        raw = np.zeros(n, dtype=np.uint8)  # bytes first: compound types with out-of-order members have no buffer view
+        if a != UNDEF and n:
+            off, _ = self.extent()
+            view = memoryview(raw)
+            done = 0
+            while done < n:
+                got = os.preadv(self._r.fd, [view[done : min(n, done + (1 << 30))]], off + done)
+                if got <= 0:
+                    raise H5LiteError(f"short read in dataset {self.name!r}")
+                done += got
+        return raw.view(self.dtype).reshape(self.shape)
 
     def read_direct(self, dest: np.ndarray) -> None:
         dest[...] = self._raw()

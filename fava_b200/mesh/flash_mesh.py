@@ -328,7 +328,7 @@ class FLASH(Structured):
         if key not in self._host_cache:
             t = self._stage(key)
             host = t.to(torch.float64).cpu().numpy()
-            if t.dim() == 3 and len(self._extent.get(key, (0, 0, 0, (0,) * 4))[3]) == 4:
+            if t.dim() == 3 and len(self._extent.get(key, (0, 0, 0, (0,) * 3))[3]) == 4:
                 host = host[None, ...]
             self._host_cache[key] = np.ascontiguousarray(np.swapaxes(host, -1, -3))
         return self._host_cache[key]
