@@ -107,6 +107,7 @@ SIGNATURES: dict[str, tuple] = {
     ),
     "fava_stage_h2d": (c_int, [c_void_p, C.c_char_p, c_i64, c_i64, c_void_p, c_void_p]),
     "fava_stage_host_h2d": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_void_p]),
+    "fava_workspace": (c_int, [c_void_p, c_int, c_i64, C.POINTER(c_void_p)]),
     "fava_ipc_export": (c_int, [c_void_p, C.POINTER(C.c_ubyte * 64)]),
     "fava_ipc_open": (c_int, [C.POINTER(C.c_ubyte * 64), C.POINTER(c_void_p)]),
     "fava_ipc_close": (c_int, [c_void_p]),

@@ -50,7 +50,7 @@ int set_error(int code, const char* fmt, ...);
 constexpr int kNumSMsB200 = 148;
 
 enum WorkspaceSlot { WS_PARTIALS = 0, WS_TABLE = 1, WS_AUX = 2, WS_FFT0 = 3, WS_FFT1 = 4, WS_FFT2 = 5,
-                     WS_FFTIN = 6, WS_COUNT = 7 };
+                     WS_FFTIN = 6, WS_BINMAP = 7, WS_USER0 = FAVA_WS_USER0, WS_COUNT = FAVA_WS_NSLOTS };
 
 struct Staging;  // pinned ring + reader threads (staging.cu)
 

@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(kBinT)
         const int tz = (int)((tile / p.ntx) % p.ntz);
         const int jl = (int)(tile / ((int64_t)p.ntx * p.ntz));
         const int j = p.ky_of_local ? p.ky_of_local[jl] : jl;
-        if (j == nh) continue;  // Nyquist ky plane: beyond the last bin
+        if (j < 0 || j == nh) continue;  // padding row / Nyquist ky plane (beyond the last bin)
         const int ky = j < nh ? j : j - n;
         const int a0 = tx * kTS, b0 = tz * kTS;
         const int lend = min(b0 + kTS - 1, n - 1);

@@ -327,3 +327,73 @@ def stage_host(arr: np.ndarray, out: torch.Tensor) -> torch.Tensor:
         "fava_stage_host_h2d",
     )
     return out
+
+
+# ---- building blocks of the slab-decomposed spectrum (raw device pointers as ints) ------------------------
+def workspace(slot: int, nbytes: int, dev=None) -> int:
+    """Context-owned cudaMalloc buffer (zero-filled when (re)allocated); returns the device address."""
+    ctx = get_context(dev)
+    p = C.c_void_p()
+    _lib.check(ctx.lib.fava_workspace(ctx.handle, int(slot), int(nbytes), C.byref(p)), "fava_workspace")
+    return int(p.value)
+
+
+def ipc_export(ptr: int) -> bytes:
+    lib = _lib.load()
+    h = (C.c_ubyte * 64)()
+    _lib.check(lib.fava_ipc_export(C.c_void_p(ptr), C.byref(h)), "fava_ipc_export")
+    return bytes(h)
+
+
+def ipc_open(handle: bytes) -> int:
+    lib = _lib.load()
+    h = (C.c_ubyte * 64).from_buffer_copy(handle)
+    p = C.c_void_p()
+    _lib.check(lib.fava_ipc_open(C.byref(h), C.byref(p)), "fava_ipc_open")
+    return int(p.value)
+
+
+def _cur_stream(dev) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def ke_weight3(rho, ux, uy, uz, wx: int, wy: int, wz: int) -> None:
+    nz, ny, nx = _check_fields(rho, ux, uy, uz)
+    ctx = get_context(rho.device)
+    _lib.check(ctx.lib.fava_ke_weight3(ctx.handle, _ptr(rho), _ptr(ux), _ptr(uy), _ptr(uz), _dtype_code(rho), nz * ny, nx,
+                                       2 * (nx // 2 + 1), C.c_void_p(wx), C.c_void_p(wy), C.c_void_p(wz), _stream(rho)),
+               "fava_ke_weight3")
+
+
+def fft_xy(data: int, nz_local: int, ny: int, nx: int, dev) -> None:
+    ctx = get_context(dev)
+    _lib.check(ctx.lib.fava_fft_xy(ctx.handle, C.c_void_p(data), nz_local, ny, nx, _cur_stream(dev)), "fava_fft_xy")
+
+
+def fft_z(data: int, nz: int, rows: int, dev) -> None:
+    ctx = get_context(dev)
+    _lib.check(ctx.lib.fava_fft_z(ctx.handle, C.c_void_p(data), nz, rows, _cur_stream(dev)), "fava_fft_z")
+
+
+def a2a_pack(src: int, peer_table: torch.Tensor, ky_of_dest: torch.Tensor, rank: int, world: int, nz_local: int, n: int,
+             nyl: int) -> None:
+    ctx = get_context(peer_table.device)
+    _lib.check(ctx.lib.fava_a2a_pack(ctx.handle, C.c_void_p(src), _ptr(peer_table), _ptr(ky_of_dest), rank, world,
+                                     nz_local, n, nyl, _stream(peer_table)), "fava_a2a_pack")
+
+
+def spectrum_bin(fx: int, fy: int, fz: int, n: int, ny_local: int, ky_of_local, local_of_ky, sums: torch.Tensor) -> None:
+    ctx = get_context(sums.device)
+    norm = 1.0 / (float(n) ** 3)
+    _lib.check(ctx.lib.fava_spectrum_bin(ctx.handle, C.c_void_p(fx), C.c_void_p(fy), C.c_void_p(fz), n, ny_local,
+                                         _ptr(ky_of_local), _ptr(local_of_ky), norm, _ptr(sums), _stream(sums)),
+               "fava_spectrum_bin")
+
+
+def spectrum_finalize(sums: torch.Tensor, n: int) -> dict[str, np.ndarray]:
+    ctx = get_context(sums.device)
+    nb = n // 2 - 1
+    bufs = [np.empty(nb, dtype=np.float64) for _ in range(4)]
+    ptrs = [b.ctypes.data_as(_lib.c_double_p) for b in bufs]
+    _lib.check(ctx.lib.fava_spectrum_finalize(ctx.handle, _ptr(sums), n, *ptrs, _stream(sums)), "fava_spectrum_finalize")
+    return dict(zip(SPECTRUM_KEYS, bufs))

@@ -25,22 +25,15 @@ class AmrPlan:
         self.total_cells = None  # int32 (3,)  NX,NY,NZ
         self.refdom_bound_box = None
 
-    def prolong_table(self, blk_beg: int, blk_end: int, z_range=None) -> device.HostTable:
-        """Leaves held by this rank (block ids relative to blk_beg) as fava_prolong_leaf rows."""
+    def slab_leaves(self, z0: int, z1: int, nzb: int):
+        """(block ids, fine-cell corners relative to the output, scales) of the selected leaves that touch
+        output planes [z0, z1), in list order (later entries win, like the reference's dict)."""
         ids = self.leaf_IDs
-        keep = (ids >= blk_beg) & (ids < blk_end)
-        ids, sc = ids[keep], self.scales[keep]
         off = self.local_BCIDs[ids, :, 0].astype(np.int64)
         if self.subdomain_flag:
             off = off - self.subdomain_BCIDs[None, :, 0]
-        return device.prolong_table(ids - blk_beg, off, sc)
-
-    def run(self, blocks, table: device.HostTable, out_zyx, z0: int, z1: int):
-        """This rank's z-slab [z0,z1) of the uniform array."""
-        nz, ny, nx = out_zyx
-        if (z0, z1) != (0, nz):
-            table.arr["off"][:, 2] -= z0
-        return device.prolong(blocks, table, (z1 - z0, ny, nx))
+        keep = (off[:, 2] < z1) & (off[:, 2] + nzb * self.scales > z0)
+        return ids[keep], off[keep], self.scales[keep]
 
 
 def build_plan(mesh, subdomain_coords: np.ndarray, refine_level: int) -> AmrPlan | None:

@@ -311,6 +311,19 @@ class FLASH(Structured):
         self._dev[key] = out
         return out
 
+    def _stage_block_range(self, key: str, b0: int, b1: int) -> torch.Tensor:
+        """Blocks [b0, b1) of a 4-D field dataset straight from the file (contiguous byte range)."""
+        if key not in self._extent:
+            raise RuntimeError(f"field {key!r} has no on-disk block dataset to stage from")
+        off, nbytes, dtype, shape = self._extent[key]
+        if len(shape) != 4:
+            raise RuntimeError("from_amr on several ranks needs a block dataset [nblocks][nzb][nyb][nxb]")
+        per = int(np.prod(shape[1:])) * dtype.itemsize
+        tdt = torch.float32 if dtype.itemsize == 4 else torch.float64
+        out = torch.empty((b1 - b0,) + tuple(shape[1:]), dtype=tdt, device=torch.device("cuda", torch.cuda.current_device()))
+        device.stage_file(self._filename, off + b0 * per, (b1 - b0) * per, out)
+        return out
+
     def device_data(self, name: str) -> torch.Tensor:
         """Device tensor of this rank's part of a field, FILE layout ([block][z][y][x] or [z][y][x])."""
         key = self._resolve(name)
@@ -442,16 +455,26 @@ class FLASH(Structured):
                 raise KeyError(nm)
             keys.append(key)
         nx, ny, nz = (int(v) for v in plan.total_cells)
+        # every rank fills its own z-slab of the uniform array from the leaves that touch it; with more
+        # than one rank those source blocks are staged as one contiguous block-id range of the file
+        z0, z1 = dist.parallel_range(nz)
+        ids, off, scales = plan.slab_leaves(z0, z1, int(self.nzb))
+        off = off - np.array([0, 0, z0], dtype=np.int64)[None, :]
         new_dev = {}
         for key in keys:
-            blocks = self.device_data(key)
-            if blocks.dim() == 3:
-                blocks = blocks[None, ...]
-            if self._part[0] != "blocks" and dist.world_size() > 1:
-                raise RuntimeError("from_amr on a single-block file is not sharded; run it on one rank")
-            table = plan.prolong_table(self.blk_beg, self.blk_end)
-            z0, z1 = dist.parallel_range(nz)
-            new_dev[key] = plan.run(blocks, table, (nz, ny, nx), z0, z1)
+            if dist.world_size() == 1:
+                blocks = self.device_data(key)
+                if blocks.dim() == 3:
+                    blocks = blocks[None, ...]
+                base = 0
+            else:
+                base, end = (int(ids.min()), int(ids.max()) + 1) if ids.size else (0, 1)
+                blocks = self._stage_block_range(key, base, end)
+            if z1 == z0:  # more ranks than output planes
+                new_dev[key] = torch.empty((0, ny, nx), dtype=torch.float64, device=blocks.device)
+                continue
+            table = device.prolong_table(ids - base, off, scales)
+            new_dev[key] = device.prolong(blocks, table, (z1 - z0, ny, nx))
         # ---- the mesh becomes a single uniform block (:1340-1361) ----
         gd = plan.grid_delta
         self._dev = new_dev

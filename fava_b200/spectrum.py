@@ -33,9 +33,83 @@ def ky_ownership(n: int, nranks: int) -> np.ndarray:
     return own
 
 
+WS_SEND = 8  # FAVA_WS_USER0 + {0,1,2}: per-component slab buffers (weight -> in-place 2-D FFT)
+WS_RECV = 11  # + {0,1,2}: per-component ky-pencil receive buffers (peer-mapped on the other ranks)
+
+
+class SlabPlan:
+    """Buffers, ky ownership tables and peer mappings of one (N, world) configuration."""
+
+    def __init__(self, n: int, rank: int, world: int, dev: torch.device):
+        if n % world or n % (2 * world):
+            raise ValueError(f"grid size {n} must be divisible by 2 x {world} ranks")
+        self.n, self.rank, self.world, self.dev = n, rank, world, dev
+        self.nxh = n // 2 + 1
+        self.nzl = n // world
+        own = ky_ownership(n, world)
+        self.nyl = own.shape[1]
+        self.ky_of_dest = torch.from_numpy(own).to(dev)
+        mine = own[rank]
+        inv = -np.ones(n, dtype=np.int32)
+        inv[mine[mine >= 0]] = np.flatnonzero(mine >= 0).astype(np.int32)
+        self.ky_of_local = torch.from_numpy(mine.copy()).to(dev)
+        self.local_of_ky = torch.from_numpy(inv).to(dev)
+        send_bytes = 16 * self.nzl * n * self.nxh
+        recv_bytes = 16 * n * self.nyl * self.nxh
+        self.send = [device.workspace(WS_SEND + c, send_bytes, dev) for c in range(3)]
+        self.recv = [device.workspace(WS_RECV + c, recv_bytes, dev) for c in range(3)]
+        # peer mappings of every rank's receive buffers (CUDA IPC; NVLink P2P under NVSwitch)
+        handles = [device.ipc_export(p) for p in self.recv]
+        gathered = [None] * world
+        torch.distributed.all_gather_object(gathered, handles)
+        self.peer_tables = []
+        self._opened = []
+        for c in range(3):
+            ptrs = []
+            for r in range(world):
+                if r == rank:
+                    ptrs.append(self.recv[c])
+                else:
+                    p = device.ipc_open(gathered[r][c])
+                    self._opened.append(p)
+                    ptrs.append(p)
+            self.peer_tables.append(torch.tensor(ptrs, dtype=torch.int64, device=dev))
+        self.sums = torch.zeros((3, n // 2 - 1), dtype=torch.float64, device=dev)
+        self.token = torch.zeros(1, dtype=torch.float32, device=dev)
+        dist.barrier()
+
+
+_plans: dict = {}
+
+
+def _plan(n: int, rank: int, world: int, dev) -> SlabPlan:
+    key = (n, rank, world, str(dev))
+    if key not in _plans:
+        _plans[key] = SlabPlan(n, rank, world, dev)
+    return _plans[key]
+
+
 def slab_ke_spectrum(rho, ux, uy, uz, n: int) -> dict[str, np.ndarray]:
     """Spectrum of the global N^3 grid formed by the ranks' z-slabs; every rank returns the full dict."""
     world, rank = dist.world_size(), dist.rank()
     if world == 1:
         return device.ke_spectrum(rho, ux, uy, uz)
-    return device.ke_spectrum_slab(rho, ux, uy, uz, n, rank, world)
+    nzl = int(rho.shape[0])
+    if nzl * world != n or tuple(rho.shape[1:]) != (n, n):
+        raise ValueError(f"rank {rank}: slab shape {tuple(rho.shape)} is not [{n // world}][{n}][{n}]")
+    p = _plan(n, rank, world, rho.device)
+    dev = rho.device
+    device.ke_weight3(rho, ux, uy, uz, *p.send)
+    for c in range(3):
+        device.fft_xy(p.send[c], p.nzl, n, n, dev)
+        device.a2a_pack(p.send[c], p.peer_tables[c], p.ky_of_dest, rank, world, p.nzl, n, p.nyl)
+    # every rank's stores into my receive buffers are complete once all ranks have passed this
+    # stream-ordered collective (it cannot finish before each rank has enqueued it after its pack kernels)
+    dist.allreduce_sum_(p.token)
+    for c in range(3):
+        device.fft_z(p.recv[c], n, p.nyl * p.nxh, dev)
+    device.spectrum_bin(p.recv[0], p.recv[1], p.recv[2], n, p.nyl, p.ky_of_local, p.local_of_ky, p.sums)
+    # shell sums and counts add across ranks; this collective also fences the receive buffers against
+    # the next call's remote stores
+    dist.allreduce_sum_(p.sums)
+    return device.spectrum_finalize(p.sums, n)

@@ -203,7 +203,13 @@ int fava_stage_h2d(fava_ctx* ctx, const char* path, int64_t file_offset, int64_t
 int fava_stage_host_h2d(fava_ctx* ctx, const void* h_src, int64_t nbytes, void* d_dst,
                         void* stream);
 
-/* ---- CUDA IPC helpers for peer-mapped exchange buffers (one process per GPU) ---------------- */
+/* ---- context-owned device buffers and CUDA IPC helpers for peer-mapped exchange buffers
+ *      (one process per GPU) ------------------------------------------------------------------------ */
+/* Grow-only device buffer owned by the context (a plain cudaMalloc allocation, so that it can be
+ * exported with fava_ipc_export); zero-filled when (re)allocated.  Slots 8..15 are free for callers. */
+#define FAVA_WS_USER0 8
+#define FAVA_WS_NSLOTS 16
+int fava_workspace(fava_ctx* ctx, int slot, int64_t bytes, void** d_ptr_out);
 int fava_ipc_export(void* d_ptr, unsigned char handle_out[64]);
 int fava_ipc_open(const unsigned char handle[64], void** d_ptr_out);
 int fava_ipc_close(void* d_ptr);
