@@ -1,11 +1,11 @@
 #!/usr/bin/env python
-"""bench.py — FAVA grid-statistics hot path on B200 (contract: see the task statement / DESIGN.md §Measurement).
+"""bench.py — FAVA grid-statistics hot path on B200 (contract: task statement; numbers explained in DESIGN.md §5).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
 
-One "step" = one pass of the hot path over one synthetic snapshot resident in HBM.  Under torchrun
-(N>1) the snapshot is split into z-slabs, one per rank ("strong" scaling: the global grid is fixed).
-Rank 0 prints ONE JSON line.
+One "step" = one pass of the hot path over one synthetic snapshot resident in HBM: Reynolds + Favre plane
+profiles along x, y and z, plus the kinetic-energy spectrum.  Under torchrun (N > 1) the SAME global grid is
+split into z-slabs, one per rank ("strong" scaling).  Rank 0 prints ONE JSON line.
 """
 
 from __future__ import annotations
@@ -28,19 +28,23 @@ METRIC = "Gcells/s & %HBM roofline: Reynolds/Favre profiles + KE spectrum @1024^
 UNIT = "Gcells/s"
 
 WORKLOADS = {
-    # name: (N, do_profiles, do_spectrum)
-    "profiles512": dict(n=512, axes=(0, 1, 2), spectrum=False,
+    "full1024": dict(n=1024, spectrum=True, cpu_n=256,
+                     desc="1024^3 uniform fp64: Reynolds + Favre stress profiles along x/y/z + kinetic_energy_spectra "
+                          "(BASELINE configs[3]; z-slab decomposed for N>1)"),
+    "full512": dict(n=512, spectrum=True, cpu_n=192, desc="512^3 uniform fp64: profiles x/y/z + kinetic_energy_spectra"),
+    "full256": dict(n=256, spectrum=True, cpu_n=128, desc="256^3 uniform fp64: profiles x/y/z + kinetic_energy_spectra (debug)"),
+    "profiles512": dict(n=512, spectrum=False, cpu_n=256,
                         desc="512^3 uniform fp64 Reynolds + Favre stress profiles along x/y/z (BASELINE configs[2])"),
-    "profiles1024": dict(n=1024, axes=(0, 1, 2), spectrum=False,
-                         desc="1024^3 uniform fp64 Reynolds + Favre stress profiles along x/y/z"),
-    "full1024": dict(n=1024, axes=(0, 1, 2), spectrum=True,
-                     desc="1024^3 uniform fp64: Reynolds + Favre profiles along x/y/z + kinetic_energy_spectra "
-                          "(BASELINE configs[3])"),
-    "full512": dict(n=512, axes=(0, 1, 2), spectrum=True,
-                    desc="512^3 uniform fp64: profiles x/y/z + kinetic_energy_spectra"),
-    "full256": dict(n=256, axes=(0, 1, 2), spectrum=True, desc="256^3 uniform fp64: profiles + spectrum (debug)"),
+    "profiles1024": dict(n=1024, spectrum=False, cpu_n=256, desc="1024^3 uniform fp64 Reynolds + Favre profiles x/y/z"),
 }
-DEFAULT_WORKLOAD = "profiles512"
+DEFAULT_WORKLOAD = "full1024"
+AXES = (0, 1, 2)
+
+# algorithmic bytes per cell (SURVEY §8d / DESIGN.md §5)
+B_PROFILE = 32.0  # rho, ux, uy, uz read once, fp64
+B_SPECTRUM = 200.0  # 3 separable line passes in Hermitian storage, weighting fused, binning incl. transposed operand
+B_WEIGHT = 32.0 + 24.0  # read 4 fields, write 3 real fp64 arrays
+B_BIN = 48.0  # 3 components x 16 B x 1/2 (r2c) x 2 (point + transposed operand)
 
 
 def measured_peak_gbs() -> tuple[float, str]:
@@ -64,7 +68,6 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.lines: list[str] = []
-        self.thread = None
 
     def start(self):
         try:
@@ -79,8 +82,8 @@ class ClockSampler:
             for line in self.proc.stdout:
                 self.lines.append(line.strip())
 
-        self.thread = threading.Thread(target=pump, daemon=True)
-        self.thread.start()
+        threading.Thread(target=pump, daemon=True).start()
+        time.sleep(0.25)  # first sample lands before the timed region starts
 
     def stop(self) -> dict:
         if self.proc is None:
@@ -106,8 +109,9 @@ class ClockSampler:
             for name, val in zip(names, f[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
+        busy = [s for s, p in zip(sm, power) if p > 0.5 * max(power)] if power else sm
         return {
-            "sm_mhz": float(np.median(sm)) if sm else None,
+            "sm_mhz": float(np.median(busy)) if busy else None,
             "sm_max_mhz": float(max(smax)) if smax else None,
             "power_w_max": float(max(power)) if power else None,
             "samples": len(sm),
@@ -119,7 +123,7 @@ class ClockSampler:
 # our arm
 # ------------------------------------------------------------------------------------------------
 def synth_slab_device(n: int, z0: int, nz: int, dev, seed: int = 1234):
-    """Synthetic snapshot slab generated directly in HBM (dens>0, sheared velocities + noise)."""
+    """Synthetic snapshot slab generated directly in HBM (dens > 0, sheared velocities + noise)."""
     import torch
 
     g = torch.Generator(device=dev)
@@ -136,10 +140,38 @@ def synth_slab_device(n: int, z0: int, nz: int, dev, seed: int = 1234):
     return rho, ux, uy, uz
 
 
+class StageTimer:
+    """CUDA-event brackets per pipeline stage, on the stream the kernels are launched on (torch's current)."""
+
+    def __init__(self):
+        self.pairs: dict[str, list] = {}
+
+    def bracket(self, name: str):
+        import torch
+
+        timer = self
+
+        class _Ctx:
+            def __enter__(self_inner):
+                self_inner.e0 = torch.cuda.Event(enable_timing=True)
+                self_inner.e1 = torch.cuda.Event(enable_timing=True)
+                self_inner.e0.record()
+
+            def __exit__(self_inner, *exc):
+                self_inner.e1.record()
+                timer.pairs.setdefault(name, []).append((self_inner.e0, self_inner.e1))
+                return False
+
+        return _Ctx()
+
+    def mean_ms(self) -> dict[str, float]:
+        return {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in self.pairs.items()}
+
+
 def run_ours(args) -> dict:
     import torch
 
-    from fava_b200 import device, dist, stats
+    from fava_b200 import device, dist, spectrum, stats
     from fava_b200.build import build_library
 
     build_library()  # no-op when the in-tree .so is current
@@ -150,77 +182,153 @@ def run_ours(args) -> dict:
     dev = torch.device("cuda", local)
     wl = WORKLOADS[args.workload]
     n = wl["n"]
-    if n % world:
-        raise SystemExit(f"grid {n} not divisible by {world} ranks")
+    if n % (2 * world):
+        raise SystemExit(f"grid {n} not divisible by 2 x {world} ranks")
     nz = n // world
     z0 = rank * nz
-    rho, ux, uy, uz = synth_slab_device(n, z0, nz, dev)
+    fields = synth_slab_device(n, z0, nz, dev)
     cell_volume = 1.0 / float(n) ** 3
     layer_volume = 1.0 / float(n)
-    ncells_global = float(n) ** 3
+    ncells = float(n) ** 3
     peak, peak_src = measured_peak_gbs()
 
-    spectrum_fn = None
-    if wl["spectrum"]:
-        from fava_b200 import spectrum as spec_mod
+    def step(f, timer: StageTimer | None = None):
+        """The public per-step path: slab profiles (x,y,z) + slab spectrum.  Returns host-readable results."""
+        out = {}
+        for ax in AXES:
+            out[ax] = stats.slab_profiles(*f, ax, cell_volume, layer_volume, favre=True, gather=False)
+        if wl["spectrum"]:
+            out["spectrum"] = spectrum.slab_ke_spectrum(*f, n)
+        return out
 
-        spectrum_fn = lambda: spec_mod.slab_ke_spectrum(rho, ux, uy, uz, n)  # noqa: E731
-
-    ev_pairs = []  # (start, stop) events bracketing the dominant kernel's launches
-
-    def step(record: bool):
-        res = {}
-        for ax in wl["axes"]:
-            if record:
-                e0 = torch.cuda.Event(enable_timing=True)
-                e1 = torch.cuda.Event(enable_timing=True)
-                piv = device.plane_pivots(ux, uy, uz, ax)
-                if ax in (0, 1):
-                    dist.broadcast_(piv, 0)
-                e0.record()
+    def step_instrumented(timer: StageTimer):
+        """Same work, stage by stage, with event brackets (used once after the timed region)."""
+        rho, ux, uy, uz = fields
+        for ax in AXES:
+            piv = device.plane_pivots(ux, uy, uz, ax)
+            if ax in (0, 1):
+                dist.broadcast_(piv, 0)
+            with timer.bracket(f"plane_moments_axis{ax}"):
                 mom, _ = device.plane_moments(rho, ux, uy, uz, ax, pivots=piv)
-                e1.record()
-                ev_pairs.append((e0, e1))
-                if ax in (0, 1):
-                    dist.allreduce_sum_(mom)
-                res[ax] = device.moments_finalize(mom, piv, cell_volume, layer_volume)
-            else:
-                res[ax] = stats.slab_profiles(rho, ux, uy, uz, ax, cell_volume, layer_volume, gather=False)
-        if spectrum_fn is not None:
-            res["spectrum"] = spectrum_fn()
-        return res
+            if ax in (0, 1):
+                dist.allreduce_sum_(mom)
+            device.moments_finalize(mom, piv, cell_volume, layer_volume)
+        if not wl["spectrum"]:
+            return
+        nxh = n // 2 + 1
+        if world == 1:
+            w = [device.workspace(3 + 1 + c, 16 * n * n * nxh, dev) for c in range(3)]  # WS_FFT1..3 of fava_ke_spectrum
+            sums = torch.zeros((3, n // 2 - 1), dtype=torch.float64, device=dev)
+            with timer.bracket("ke_weight3"):
+                device.ke_weight3(rho, ux, uy, uz, *w)
+            for c in range(3):
+                with timer.bracket("cufft_xy"):
+                    device.fft_xy(w[c], n, n, n, dev)
+                with timer.bracket("cufft_z"):
+                    device.fft_z(w[c], n, n * nxh, dev)
+            with timer.bracket("spectrum_bin"):
+                device.spectrum_bin(w[0], w[1], w[2], n, n, None, None, sums)
+        else:
+            p = spectrum._plan(n, rank, world, dev)
+            with timer.bracket("ke_weight3"):
+                device.ke_weight3(rho, ux, uy, uz, *p.send)
+            for c in range(3):
+                with timer.bracket("cufft_xy"):
+                    device.fft_xy(p.send[c], p.nzl, n, n, dev)
+                with timer.bracket("a2a_pack"):
+                    device.a2a_pack(p.send[c], p.peer_tables[c], p.ky_of_dest, rank, world, p.nzl, n, p.nyl)
+            dist.allreduce_sum_(p.token)
+            for c in range(3):
+                with timer.bracket("cufft_z"):
+                    device.fft_z(p.recv[c], n, p.nyl * p.nxh, dev)
+            with timer.bracket("spectrum_bin"):
+                device.spectrum_bin(p.recv[0], p.recv[1], p.recv[2], n, p.nyl, p.ky_of_local, p.local_of_ky, p.sums)
+            dist.allreduce_sum_(p.sums)
 
     for _ in range(args.warmup):
-        step(False)
+        step(fields)
     torch.cuda.synchronize()
 
     sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
     launches0 = device.launch_count()
     dist.barrier()
     torch.cuda.synchronize()
-    if sampler:
-        sampler.start()
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
     for _ in range(args.steps):
-        step(True)
+        step(fields)
     t1.record()
     torch.cuda.synchronize()
     dist.barrier()
-    clocks = sampler.stop() if sampler else None
     launches = device.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
     elapsed_ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
     dist.allreduce_max_(elapsed_ms)
     ms_per_step = float(elapsed_ms.item()) / args.steps
-    value = ncells_global / (ms_per_step * 1e-3) / 1e9
+    value = ncells / (ms_per_step * 1e-3) / 1e9
 
-    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev_pairs]))
-    algo_bytes = 32.0 * float(nz) * n * n  # 4 fp64 fields read once (4*s bytes per cell per call)
-    achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
+    # ---- per-stage device times (same kernels, event-bracketed, after the timed region) -------------
+    timer = StageTimer()
+    for _ in range(2):
+        step_instrumented(timer)
+    torch.cuda.synchronize()
+    stage_ms = timer.mean_ms()
+    local_cells = ncells / world
+    stages = {}
+    for name, ms in stage_ms.items():
+        if name.startswith("plane_moments"):
+            algo = B_PROFILE * local_cells
+        elif name == "ke_weight3":
+            algo = B_WEIGHT * local_cells
+        elif name == "spectrum_bin":
+            algo = B_BIN * local_cells
+        elif name in ("cufft_xy", "cufft_z"):
+            algo = None  # library call (cuFFT), not our kernel
+        elif name == "a2a_pack":
+            algo = 8.0 * local_cells  # one complex r2c row set read once; (world-1)/world of it crosses NVLink
+        else:
+            algo = None
+        stages[name] = {"ms": ms, "launches_per_step": len(timer.pairs[name]) // 2}
+        if algo is not None:
+            stages[name]["algorithmic_bytes"] = algo
+            stages[name]["achieved_gbs"] = algo / (ms * 1e-3) / 1e9
+            stages[name]["frac_of_hbm_peak"] = stages[name]["achieved_gbs"] / peak
+    if "a2a_pack" in stages:
+        stages["a2a_pack"]["nvlink_gbs_per_gpu"] = 8.0 * local_cells * (world - 1) / world / (stages["a2a_pack"]["ms"] * 1e-3) / 1e9
+        stages["a2a_pack"]["frac_of_nvlink_770"] = stages["a2a_pack"]["nvlink_gbs_per_gpu"] / 770.0
 
-    # ---- e2e: host buffers, H2D inside the timed region, result read back ---------------------
-    e2e = run_e2e(args, wl, dev, rank, world, (rho, ux, uy, uz), cell_volume, layer_volume, spectrum_fn is not None)
+    # dominant kernel of OUR code (time per step = ms x launches per step)
+    own = {k: v for k, v in stages.items() if "algorithmic_bytes" in v and k != "a2a_pack"}
+    dom = max(own, key=lambda k: own[k]["ms"] * own[k]["launches_per_step"])
+    kernel_names = {"spectrum_bin": "k_spectrum_bin (fava_spectrum_bin)", "ke_weight3": "k_ke_weight3 (fava_ke_weight3)"}
+    traffic = load_profile_traffic(dom)
+    roofline = {
+        "kernel": kernel_names.get(dom, "k_moments_cols/k_moments_rows (fava_plane_moments), " + dom),
+        "bound": "hbm",
+        "achieved": own[dom]["achieved_gbs"],
+        "peak": peak,
+        "unit": "GB/s",
+        "frac": own[dom]["achieved_gbs"] / peak,
+        "traffic": traffic,
+        "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": own[dom]["algorithmic_bytes"],
+        "kernel_ms": own[dom]["ms"],
+        "note": "dominant hand-written kernel by time per step; every stage is listed under roofline_stages "
+                "(cuFFT passes are library calls and carry no roofline claim)",
+    }
+    prof_ms = sum(v["ms"] for k, v in stages.items() if k.startswith("plane_moments"))
+    summary = {"profiles_xyz": {"ms": prof_ms, "achieved_gbs": 3 * B_PROFILE * local_cells / (prof_ms * 1e-3) / 1e9}}
+    summary["profiles_xyz"]["frac_of_hbm_peak"] = summary["profiles_xyz"]["achieved_gbs"] / peak
+    if wl["spectrum"]:
+        spec_ms = sum(v["ms"] * v["launches_per_step"] for k, v in stages.items() if not k.startswith("plane_moments"))
+        summary["ke_spectrum"] = {"ms": spec_ms, "model_bytes_per_cell": B_SPECTRUM,
+                                  "achieved_gbs": B_SPECTRUM * local_cells / (spec_ms * 1e-3) / 1e9}
+        summary["ke_spectrum"]["frac_of_hbm_peak"] = summary["ke_spectrum"]["achieved_gbs"] / peak
+
+    e2e = run_e2e(args, wl, dev, rank, world, fields, step)
 
     out = {
         "metric": METRIC,
@@ -239,90 +347,82 @@ def run_ours(args) -> dict:
             "workload": wl["desc"],
             "grid": [n, n, n],
             "parallelism": f"z-slabs x{world}",
-            "l2": "inputs (4 fields x %.1f GiB per GPU) exceed the 126 MB L2; no flush needed" % (8.0 * nz * n * n / 2**30),
+            "l2": "inputs (4 fields x %.2f GiB per GPU) exceed the 126 MB L2; no flush needed" % (8.0 * nz * n * n / 2**30),
         },
         "e2e": e2e,
         "gpu_launches": int(launches),
-        "roofline": {
-            "kernel": "k_moments_{cols,rows} (fava_plane_moments, one launch per axis; mean over x,y,z launches)",
-            "bound": "hbm",
-            "achieved": achieved,
-            "peak": peak,
-            "unit": "GB/s",
-            "frac": achieved / peak,
-            "traffic": load_profile_traffic(),
-            "peak_source": peak_src,
-            "algorithmic_bytes_per_launch": algo_bytes,
-            "kernel_ms": kern_ms,
-        },
+        "roofline": roofline,
+        "roofline_stages": stages,
+        "roofline_summary": summary,
         "clocks": clocks,
     }
-    if rank == 0:
-        out["cpu_baseline"] = cpu_baseline(args, wl)
+    if rank == 0 and world == 1:
+        out["cpu_baseline"] = cpu_baseline(wl)
     return out if rank == 0 else {}
 
 
-def run_e2e(args, wl, dev, rank, world, dev_fields, cell_volume, layer_volume, with_spectrum) -> dict:
-    """Same step through host buffers: pinned host -> H2D -> kernels -> D2H of the profiles."""
+def run_e2e(args, wl, dev, rank, world, dev_fields, step) -> dict:
+    """Same step through HOST buffers: pinned host fields -> H2D (in the timed region) -> public step ->
+    profiles and spectrum read back to the host."""
     import torch
 
-    from fava_b200 import dist, stats
+    from fava_b200 import dist
 
-    n = wl["n"]
-    nz = n // world
     host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in dev_fields]
     for h, d in zip(host, dev_fields):
         h.copy_(d)
     stage = [torch.empty_like(t) for t in dev_fields]
     torch.cuda.synchronize()
     h2d = sum(h.numel() * h.element_size() for h in host)
-    d2h_holder = {}
+    d2h = {"bytes": 0}
 
     def e2e_step():
         for h, s in zip(host, stage):
             s.copy_(h, non_blocking=True)
-        res = []
-        for ax in wl["axes"]:
-            out = stats.slab_profiles(*stage, ax, cell_volume, layer_volume, gather=False)
-            res.extend(v.cpu() for v in out.values())
-        if with_spectrum:
-            from fava_b200 import spectrum as spec_mod
-
-            sp = spec_mod.slab_ke_spectrum(*stage, n)
-            res.extend(np.asarray(v) for v in sp.values())
-        d2h_holder["bytes"] = sum(int(getattr(r, "nbytes", 0)) if isinstance(r, np.ndarray)
-                                  else r.numel() * r.element_size() for r in res)
-        return res
+        res = step(stage)
+        nbytes = 0
+        for key, val in res.items():
+            if key == "spectrum":
+                nbytes += sum(v.nbytes for v in val.values())  # already on the host (fava_spectrum_finalize)
+            else:
+                hostv = {k: v.cpu() for k, v in val.items()}
+                nbytes += sum(v.numel() * v.element_size() for v in hostv.values())
+        d2h["bytes"] = nbytes
 
     e2e_step()
+    steps = max(1, min(args.steps, 3))
     dist.barrier()
     torch.cuda.synchronize()
-    steps = max(1, min(args.steps, 5))
-    t0 = time.perf_counter()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
     for _ in range(steps):
         e2e_step()
+    e1.record()
     torch.cuda.synchronize()
     dist.barrier()
-    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    dt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     dist.allreduce_max_(dt)
-    sec = float(dt.item()) / steps
+    ms = float(dt.item()) / steps
+    n = wl["n"]
     return {
-        "value": float(n) ** 3 / sec / 1e9,
+        "value": float(n) ** 3 / (ms * 1e-3) / 1e9,
         "unit": UNIT,
-        "h2d_bytes_per_step": int(h2d),
-        "d2h_bytes_per_step": int(d2h_holder.get("bytes", 0)),
-        "ms_per_step": sec * 1e3,
+        "h2d_bytes_per_step": int(h2d) * world,
+        "d2h_bytes_per_step": int(d2h["bytes"]),
+        "ms_per_step": ms,
         "steps": steps,
-        "note": "pinned host fp64 fields -> cudaMemcpyAsync -> kernels -> profiles copied back; per-rank bytes",
+        "note": "pinned host fp64 fields -> cudaMemcpyAsync -> slab profiles x/y/z + slab spectrum -> results on the "
+                "host; PCIe-bound (h2d bytes are the whole-job total over all ranks)",
     }
 
 
-def load_profile_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+def load_profile_traffic(stage: str):
+    """dram bytes per launch of a kernel from the committed ncu capture (profiles/traffic.json), if any."""
     p = ROOT / "profiles" / "traffic.json"
     if p.exists():
         try:
-            return json.loads(p.read_text()).get("plane_moments_bytes_per_launch")
+            return json.loads(p.read_text()).get(stage)
         except Exception:
             return None
     return None
@@ -331,8 +431,9 @@ def load_profile_traffic():
 # ------------------------------------------------------------------------------------------------
 # CPU baseline / reference arm: the oracle port of the reference's NumPy algorithm
 # ------------------------------------------------------------------------------------------------
-def _cpu_sample(n_sample: int, axes, spectrum: bool, seed: int = 1234):
-    """Time the reference algorithm (oracle port) on an n_sample^3 fp64 single-block snapshot."""
+def _cpu_sample(n_sample: int, spectrum: bool, seed: int = 1234) -> float:
+    """Time the reference algorithm (oracle port, bit-identical to the reference on the golden vectors) on an
+    n_sample^3 fp64 single-block snapshot: reynolds_stress along x/y/z (+ kinetic_energy_spectra)."""
     from oracle import fava_oracle as orc
 
     rng = np.random.default_rng(seed)
@@ -348,26 +449,26 @@ def _cpu_sample(n_sample: int, axes, spectrum: bool, seed: int = 1234):
     geom = orc.uniform_geom(shape, bbox_dtype=np.float64)
     data4 = {k: v[None, ...] for k, v in data3.items()}
     t0 = time.perf_counter()
-    for ax in axes:
+    for ax in AXES:
         orc.reynolds_stress(geom, data4, axis=ax)
     if spectrum:
         orc.kinetic_energy_spectra(data3, shape)
     return time.perf_counter() - t0
 
 
-def cpu_baseline(args, wl) -> dict:
-    n_s = 256 if not wl["spectrum"] else 192
-    sec = _cpu_sample(n_s, wl["axes"], wl["spectrum"])
-    return {
-        "value": float(n_s) ** 3 / sec / 1e9,
-        "unit": UNIT,
-        "cores": 1,
-        "kind": "port",
-        "sample": f"{n_s}^3 fp64 single-block snapshot, same step (reynolds_stress x/y/z"
-                  f"{' + kinetic_energy_spectra' if wl['spectrum'] else ''}), NumPy port of the reference "
-                  f"algorithm (oracle/fava_oracle.py), fields preloaded, {sec:.2f} s; host has {os.cpu_count()} cpus, "
-                  "the reference parallelises only over MPI ranks/blocks so one block = one core",
-    }
+def _cpu_sample_text(n_s: int, wl, sec: float) -> str:
+    return (f"{n_s}^3 fp64 single-block sample of the workload (reynolds_stress x/y/z"
+            f"{' + kinetic_energy_spectra' if wl['spectrum'] else ''}), NumPy port of the reference algorithm "
+            f"(oracle/fava_oracle.py; the reference itself is pure NumPy/SciPy), fields preloaded, {sec:.2f} s per "
+            f"step; 1 process = 1 core: the reference parallelises only over MPI ranks (none here) and needs "
+            f"~230 B/cell for the spectrum, so 1024^3 cannot run on a host; host has {os.cpu_count()} cpus")
+
+
+def cpu_baseline(wl) -> dict:
+    n_s = wl["cpu_n"]
+    sec = _cpu_sample(n_s, wl["spectrum"])
+    return {"value": float(n_s) ** 3 / sec / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": _cpu_sample_text(n_s, wl, sec)}
 
 
 def run_reference(args) -> dict:
@@ -375,15 +476,14 @@ def run_reference(args) -> dict:
     if rank != 0:
         return {}
     wl = WORKLOADS[args.workload]
-    n_s = 256 if not wl["spectrum"] else 192
+    n_s = wl["cpu_n"]
     for _ in range(min(args.warmup, 1)):
-        _cpu_sample(64, wl["axes"], wl["spectrum"])
+        _cpu_sample(64, wl["spectrum"])
     steps = max(1, min(args.steps, 3))
-    secs = [_cpu_sample(n_s, wl["axes"], wl["spectrum"]) for _ in range(steps)]
+    secs = [_cpu_sample(n_s, wl["spectrum"]) for _ in range(steps)]
     sec = float(np.mean(secs))
     value = float(n_s) ** 3 / sec / 1e9
-    sample = (f"{n_s}^3 fp64 single-block sample of the workload per step (the reference needs ~230 B/cell and hours at "
-              f"1024^3), NumPy port of the reference algorithm, 1 process")
+    sample = _cpu_sample_text(n_s, wl, sec)
     return {
         "impl": "reference",
         "metric": METRIC,
@@ -398,7 +498,7 @@ def run_reference(args) -> dict:
         "vs_baseline": None,
         "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": wl["desc"], "sample": sample},
+        "config": {"workload": wl["desc"], "grid": [wl["n"]] * 3, "sample": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
