@@ -194,12 +194,7 @@ def run_ours(args) -> dict:
 
     def step(f, timer: StageTimer | None = None):
         """The public per-step path: slab profiles (x,y,z) + slab spectrum.  Returns host-readable results."""
-        out = {}
-        for ax in AXES:
-            out[ax] = stats.slab_profiles(*f, ax, cell_volume, layer_volume, favre=True, gather=False)
-        if wl["spectrum"]:
-            out["spectrum"] = spectrum.slab_ke_spectrum(*f, n)
-        return out
+        return stats.slab_step(*f, n, cell_volume, layer_volume, axes=AXES, spectrum=wl["spectrum"], favre=True)
 
     def step_instrumented(timer: StageTimer):
         """Same work, stage by stage, with event brackets (used once after the timed region)."""
@@ -237,7 +232,7 @@ def run_ours(args) -> dict:
                     device.fft_xy(p.send[c], p.nzl, n, n, dev)
                 with timer.bracket("a2a_pack"):
                     device.a2a_pack(p.send[c], p.peer_tables[c], p.ky_of_dest, rank, world, p.nzl, n, p.nyl)
-            dist.allreduce_sum_(p.token)
+            dist.allreduce_sum_(p.tokens[0])
             for c in range(3):
                 with timer.bracket("cufft_z"):
                     device.fft_z(p.recv[c], n, p.nyl * p.nxh, dev)

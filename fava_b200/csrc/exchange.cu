@@ -9,25 +9,44 @@
 // [z][ky_local][kx] order the strided z-transform and the binning kernel consume.  16-byte coalesced
 // loads and stores; the NVLink stores of one row overlap the loads of the next.
 // Ownership is +-ky symmetric (fava_b200/spectrum.py:ky_ownership), padding rows (-1) are skipped.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace fava {
 
-__global__ void __launch_bounds__(128)
+// Persistent form: a SMALL grid (default 48 CTAs, FAVA_A2A_CTAS) walks all rows, so the kernel occupies only a
+// fraction of the SMs and — launched on a high-priority side stream — runs BESIDE the HBM-bound FFT / moment
+// kernels instead of queueing behind them; NVLink (~0.6 TB/s) needs far fewer SMs than HBM does.
+constexpr int kPackThreads = 512;
+constexpr int kPackWarps = kPackThreads / 32;
+constexpr int kPackUnroll = 16;  // 16 x 16 B per lane = one 8 KB row (N = 1024) per warp in flight
+
+__global__ void __launch_bounds__(kPackThreads)
     k_a2a_pack(const double2* __restrict__ in, double2* const* __restrict__ peer_recv,
                const int32_t* __restrict__ ky_of_dest, int me, int nranks, int nz_local, int n, int nyl, int nxh) {
-    // blockIdx.x = ((zl * nranks) + dest) * nyl + jl
-    const int64_t id = blockIdx.x + (int64_t)blockIdx.y * gridDim.x;
+    const int lane = threadIdx.x & 31;
     const int64_t total = (int64_t)nz_local * nranks * nyl;
-    if (id >= total) return;
-    const int jl = (int)(id % nyl);
-    const int dest = (int)((id / nyl) % nranks);
-    const int zl = (int)(id / ((int64_t)nyl * nranks));
-    const int j = ky_of_dest[dest * nyl + jl];
-    if (j < 0) return;
-    const double2* src = in + ((int64_t)zl * n + j) * nxh;
-    double2* dst = peer_recv[dest] + (((int64_t)me * nz_local + zl) * nyl + jl) * nxh;
-    for (int x = threadIdx.x; x < nxh; x += blockDim.x) dst[x] = __ldcs(src + x);
+    const int64_t stride = (int64_t)gridDim.x * kPackWarps;
+    // one warp per ky row; destination-major order staggered by rank: at any time the ranks write to different peers
+    for (int64_t it = (int64_t)blockIdx.x * kPackWarps + (threadIdx.x >> 5); it < total; it += stride) {
+        const int jl = (int)(it % nyl);
+        const int zl = (int)((it / nyl) % nz_local);
+        const int dest = (int)((it / ((int64_t)nyl * nz_local) + me) % nranks);
+        const int j = ky_of_dest[dest * nyl + jl];
+        if (j < 0) continue;
+        const double2* src = in + ((int64_t)zl * n + j) * nxh;
+        double2* dst = peer_recv[dest] + (((int64_t)me * nz_local + zl) * nyl + jl) * nxh;
+        int x = lane;
+        for (; x + (kPackUnroll - 1) * 32 < nxh; x += kPackUnroll * 32) {
+            double2 v[kPackUnroll];
+#pragma unroll
+            for (int u = 0; u < kPackUnroll; ++u) v[u] = __ldcs(src + x + u * 32);
+#pragma unroll
+            for (int u = 0; u < kPackUnroll; ++u) dst[x + u * 32] = v[u];
+        }
+        for (; x < nxh; x += 32) dst[x] = __ldcs(src + x);
+    }
 }
 
 }  // namespace fava
@@ -43,9 +62,13 @@ int fava_a2a_pack(fava_ctx* ctx, const double* d_in, double* const* d_peer_recv,
     FAVA_REQUIRE(nz_local > 0 && n > 1 && (n & 1) == 0 && nyl > 0, "fava_a2a_pack: bad shape");
     DeviceGuard g(ctx->device);
     const int64_t total = nz_local * nranks * nyl;
-    const unsigned gx = (unsigned)std::min<int64_t>(total, 65535 * 16);
-    const unsigned gy = (unsigned)((total + gx - 1) / gx);
-    k_a2a_pack<<<dim3(gx, gy), 128, 0, (cudaStream_t)stream>>>((const double2*)d_in, (double2* const*)d_peer_recv,
+    static const int env_ctas = [] {
+        const char* e = getenv("FAVA_A2A_CTAS");
+        return e ? atoi(e) : 0;
+    }();
+    const int want = env_ctas > 0 ? env_ctas : 48;
+    const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(total, want));
+    k_a2a_pack<<<gx, kPackThreads, 0, (cudaStream_t)stream>>>((const double2*)d_in, (double2* const*)d_peer_recv,
                                                               d_ky_of_dest, my_rank, nranks, (int)nz_local, (int)n,
                                                               (int)nyl, (int)(n / 2 + 1));
     FAVA_LAUNCHED();

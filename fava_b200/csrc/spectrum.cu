@@ -84,25 +84,33 @@ __device__ __forceinline__ int shell_of(int k2) {
     return m;
 }
 
-__global__ void __launch_bounds__(kBinT)
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+    // 16-byte global -> shared copy that bypasses registers (LDGSTS); src-size 0 zero-fills the destination
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+}
+
+// dynamic shared memory: [3][nbins] CTA bins | [3][32][33] transposed operand tiles | [3][8][64] warp bins
+__global__ void __launch_bounds__(kBinT, 2)
     k_spectrum_bin(const double2* __restrict__ fx, const double2* __restrict__ fy, const double2* __restrict__ fz,
                    BinParams p, double* __restrict__ partial) {
-    extern __shared__ double dyn[];  // [tot nbins][lon nbins][cnt nbins]
+    extern __shared__ __align__(16) unsigned char dyn_raw[];
+    double* dyn = reinterpret_cast<double*>(dyn_raw);
+    const int nb_pad = (3 * p.nbins + 1) & ~1;  // keep the tiles 16-byte aligned
     double* cta_tot = dyn;
     double* cta_lon = dyn + p.nbins;
     double* cta_cnt = dyn + 2 * p.nbins;
-    __shared__ double2 S[kTS][kTS + 1];
-    __shared__ double wb_tot[kBinWarps][kSlots];
-    __shared__ double wb_lon[kBinWarps][kSlots];
-    __shared__ double wb_cnt[kBinWarps][kSlots];
+    typedef double2 Tile[kTS][kTS + 1];
+    Tile* S = reinterpret_cast<Tile*>(dyn + nb_pad);
+    double* wb = reinterpret_cast<double*>(S + 3);  // [3][kBinWarps][kSlots]
+    double(*wb_tot)[kSlots] = reinterpret_cast<double(*)[kSlots]>(wb);
+    double(*wb_lon)[kSlots] = reinterpret_cast<double(*)[kSlots]>(wb + kBinWarps * kSlots);
+    double(*wb_cnt)[kSlots] = reinterpret_cast<double(*)[kSlots]>(wb + 2 * kBinWarps * kSlots);
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     for (int i = t; i < 3 * p.nbins; i += kBinT) dyn[i] = 0.0;
-    for (int i = t; i < kBinWarps * kSlots; i += kBinT) {
-        (&wb_tot[0][0])[i] = 0.0;
-        (&wb_lon[0][0])[i] = 0.0;
-        (&wb_cnt[0][0])[i] = 0.0;
-    }
+    for (int i = t; i < 3 * kBinWarps * kSlots; i += kBinT) wb[i] = 0.0;
     __syncthreads();
 
     const int n = p.n, nh = n >> 1;
@@ -125,65 +133,66 @@ __global__ void __launch_bounds__(kBinT)
         const int jm = (n - j) % n;
         const int jml = p.local_of_ky ? p.local_of_ky[jm] : jm;
 
-        // this thread's points: kx = a0 + lane, kz rows b0 + warp + 8 i
-        const int kx = a0 + lane;
-        double lre[4], lim[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) lre[i] = lim[i] = 0.0;
-        double tot[4] = {0.0, 0.0, 0.0, 0.0};
-
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            // transposed operand tile: S[a][b] = u^_c at (x-wn = kz(b), y-wn = ky, z-wn = kx(a))
+        // ---- phase A: all three transposed operand tiles in flight (no registers held) -------------------
+        // S[c][a][b] = stored value whose (conjugate, if kz(b) < 0) is u^_c at (x-wn = kz(b), y-wn = ky, z-wn = kx(a))
+        {
+            const int l = b0 + lane;  // kz index handled by this lane while loading
+            const bool lok = l < n && l != nh;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int a = warp + kBinWarps * i;  // kx_local (row being loaded)
+                const int a = warp + kBinWarps * i;  // kx_local of the row being loaded
                 const int kxa = a0 + a;
-                const int l = b0 + lane;             // kz index of this lane
-                double2 v = make_double2(0.0, 0.0);
-                if (kxa < nh && l < n && l != nh) {
-                    if (l < nh) {
-                        v = F[c][(int64_t)kxa * p.zstride + (int64_t)jl * p.nxh + l];
-                    } else {
-                        const int zi = (n - kxa) % n;
-                        v = F[c][(int64_t)zi * p.zstride + (int64_t)jml * p.nxh + (n - l)];
-                        v.y = -v.y;
-                    }
-                }
-                S[a][lane] = v;
+                const bool ok = lok && kxa < nh;
+                int64_t off = 0;
+                if (ok) off = l < nh ? (int64_t)kxa * p.zstride + (int64_t)jl * p.nxh + l
+                                     : (int64_t)((n - kxa) % n) * p.zstride + (int64_t)jml * p.nxh + (n - l);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) cp_async16(&S[c][a][lane], F[c] + off, ok);
             }
-            __syncthreads();
+            asm volatile("cp.async.commit_group;\n" ::);
+        }
+        // ---- phase B: this thread's own points: kx = a0 + lane, kz rows b0 + warp + 8 i ------------------
+        const int kx = a0 + lane;
+        double tot[4];
+        {
+            double2 d[3][4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int b = warp + kBinWarps * i;  // kz_local
-                const int l = b0 + b;
-                if (kx < nh && l < n && l != nh) {
-                    const int kz = l < nh ? l : l - n;
-                    const double kc = c == 0 ? (double)kx : (c == 1 ? (double)ky : (double)kz);
-                    const double2 tv = S[lane][b];
-                    lre[i] = fma(kc, tv.x, lre[i]);
-                    lim[i] = fma(kc, tv.y, lim[i]);
-                    const double2 d = F[c][(int64_t)l * p.zstride + (int64_t)jl * p.nxh + kx];
-                    tot[i] += d.x * d.x + d.y * d.y;
-                }
+                const int l = b0 + warp + kBinWarps * i;
+                const bool ok = kx < nh && l < n && l != nh;
+                const int64_t off = ok ? (int64_t)l * p.zstride + (int64_t)jl * p.nxh + kx : 0;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) d[c][i] = ok ? __ldcs(F[c] + off) : make_double2(0.0, 0.0);
             }
-            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                tot[i] = 0.0;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) tot[i] += d[c][i].x * d[c][i].x + d[c][i].y * d[c][i].y;
+            }
         }
+        asm volatile("cp.async.wait_group 0;\n" ::);
+        __syncthreads();
 
-        // shell-wise warp reduction of the 4 rows
+        // ---- phase C: projection, shell index, warp-level segmented reduction ---------------------------
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int l = b0 + warp + kBinWarps * i;
+            const int b = warp + kBinWarps * i;  // kz_local
+            const int l = b0 + b;
             int key = -1;
             double vt = 0.0, vl = 0.0, vc = 0.0;
             if (kx < nh && l < n && l != nh) {
                 const int kz = l < nh ? l : l - n;
                 const int k2 = kx * kx + ky * ky + kz * kz;
                 if (k2 <= p.kmax2) {
+                    const double sgn = l < nh ? 1.0 : -1.0;  // conjugate of the folded half
+                    const double2 t0 = S[0][lane][b], t1 = S[1][lane][b], t2 = S[2][lane][b];
+                    const double lre = fma((double)kx, t0.x, fma((double)ky, t1.x, (double)kz * t2.x));
+                    const double lim = sgn * fma((double)kx, t0.y, fma((double)ky, t1.y, (double)kz * t2.y));
                     key = shell_of(k2);
                     const double w = kx == 0 ? 1.0 : 2.0;
                     vt = w * 0.5 * tot[i] * p.norm2;
-                    vl = k2 > 0 ? w * (lre[i] * lre[i] + lim[i] * lim[i]) / (double)k2 * p.norm2 : 0.0;
+                    vl = k2 > 0 ? w * (lre * lre + lim * lim) / (double)k2 * p.norm2 : 0.0;
                     vc = w;
                 }
             }
@@ -205,7 +214,7 @@ __global__ void __launch_bounds__(kBinT)
             }
             __syncwarp();
         }
-        __syncthreads();
+        __syncthreads();  // tiles consumed, warp bins complete
         if (t < kSlots) {
             double st = 0.0, sl = 0.0, sc = 0.0;
 #pragma unroll
@@ -216,8 +225,9 @@ __global__ void __launch_bounds__(kBinT)
             const int m = mlo + t;
             if (m < p.nbins && sc != 0.0) cta_tot[m] += st, cta_lon[m] += sl, cta_cnt[m] += sc;
         }
-        __syncthreads();
+        // the next tile's first __syncthreads (after its loads) orders these bin updates
     }
+    __syncthreads();
     double* out = partial + (int64_t)blockIdx.x * 3 * p.nbins;
     for (int i = t; i < 3 * p.nbins; i += kBinT) out[i] = dyn[i];
 }
@@ -359,13 +369,13 @@ int fava_spectrum_bin(fava_ctx* ctx, const double* d_fx, const double* d_fy, con
     p.zstride = ny_local * (int64_t)p.nxh;
     p.ky_of_local = d_ky_of_local, p.local_of_ky = d_local_of_ky;
     p.norm2 = norm * norm;
-    const size_t dyn = sizeof(double) * 3 * (size_t)p.nbins;
-    const int ncta = (int)std::min<int64_t>(p.ntiles, (int64_t)ctx->num_sms * 4);
+    const size_t nb_pad = (size_t)((3 * p.nbins + 1) & ~1);
+    const size_t dyn = sizeof(double) * (nb_pad + 3 * kBinWarps * kSlots) + 3 * sizeof(double2) * kTS * (kTS + 1);
+    const int ncta = (int)std::min<int64_t>(p.ntiles, (int64_t)ctx->num_sms * 2);
     void* ws;
     rc = ctx_workspace(ctx, WS_PARTIALS, sizeof(double) * 3 * (size_t)p.nbins * ncta, &ws);
     if (rc) return rc;
-    if (dyn > 16 * 1024)
-        FAVA_CHECK_CUDA(cudaFuncSetAttribute(k_spectrum_bin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    FAVA_CHECK_CUDA(cudaFuncSetAttribute(k_spectrum_bin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     k_spectrum_bin<<<ncta, kBinT, dyn, st>>>((const double2*)d_fx, (const double2*)d_fy, (const double2*)d_fz, p,
                                             (double*)ws);
     FAVA_LAUNCHED();

@@ -75,7 +75,10 @@ class SlabPlan:
                     ptrs.append(p)
             self.peer_tables.append(torch.tensor(ptrs, dtype=torch.int64, device=dev))
         self.sums = torch.zeros((3, n // 2 - 1), dtype=torch.float64, device=dev)
-        self.token = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.tokens = [torch.zeros(1, dtype=torch.float32, device=dev) for _ in range(3)]
+        self.comm_stream = torch.cuda.Stream(device=dev, priority=-1)  # NVLink exchange runs beside the HBM-bound kernels
+        self.ev_xy = [torch.cuda.Event() for _ in range(3)]
+        self.ev_done = [torch.cuda.Event() for _ in range(3)]
         dist.barrier()
 
 
@@ -89,27 +92,42 @@ def _plan(n: int, rank: int, world: int, dev) -> SlabPlan:
     return _plans[key]
 
 
-def slab_ke_spectrum(rho, ux, uy, uz, n: int) -> dict[str, np.ndarray]:
-    """Spectrum of the global N^3 grid formed by the ranks' z-slabs; every rank returns the full dict."""
+def slab_ke_spectrum(rho, ux, uy, uz, n: int, overlap=None) -> dict[str, np.ndarray]:
+    """Spectrum of the global N^3 grid formed by the ranks' z-slabs; every rank returns the full dict.
+
+    Schedule: the exchange of component c (K5, NVLink-bound, on a side stream) overlaps the 2-D transforms
+    of component c+1 and whatever `overlap()` enqueues on the calling stream (bench.py and
+    stats.slab_step put the HBM-bound plane-profile kernels there); the z-transform of component c
+    starts as soon as ITS exchange has completed on every rank."""
     world, rank = dist.world_size(), dist.rank()
     if world == 1:
+        if overlap is not None:
+            overlap()
         return device.ke_spectrum(rho, ux, uy, uz)
     nzl = int(rho.shape[0])
     if nzl * world != n or tuple(rho.shape[1:]) != (n, n):
         raise ValueError(f"rank {rank}: slab shape {tuple(rho.shape)} is not [{n // world}][{n}][{n}]")
     p = _plan(n, rank, world, rho.device)
     dev = rho.device
+    cur = torch.cuda.current_stream(dev)
     device.ke_weight3(rho, ux, uy, uz, *p.send)
     for c in range(3):
         device.fft_xy(p.send[c], p.nzl, n, n, dev)
-        device.a2a_pack(p.send[c], p.peer_tables[c], p.ky_of_dest, rank, world, p.nzl, n, p.nyl)
-    # every rank's stores into my receive buffers are complete once all ranks have passed this
-    # stream-ordered collective (it cannot finish before each rank has enqueued it after its pack kernels)
-    dist.allreduce_sum_(p.token)
+        p.ev_xy[c].record(cur)
+        with torch.cuda.stream(p.comm_stream):
+            p.comm_stream.wait_event(p.ev_xy[c])
+            device.a2a_pack(p.send[c], p.peer_tables[c], p.ky_of_dest, rank, world, p.nzl, n, p.nyl)
+            # every rank's stores of component c into my receive buffer are complete once all ranks have
+            # passed this stream-ordered collective (each enqueues it after its own pack kernel)
+            dist.allreduce_sum_(p.tokens[c])
+            p.ev_done[c].record(p.comm_stream)
+    if overlap is not None:
+        overlap()
     for c in range(3):
+        cur.wait_event(p.ev_done[c])
         device.fft_z(p.recv[c], n, p.nyl * p.nxh, dev)
     device.spectrum_bin(p.recv[0], p.recv[1], p.recv[2], n, p.nyl, p.ky_of_local, p.local_of_ky, p.sums)
     # shell sums and counts add across ranks; this collective also fences the receive buffers against
-    # the next call's remote stores
+    # the next call's remote stores (a rank's next pack is stream-ordered after it)
     dist.allreduce_sum_(p.sums)
     return device.spectrum_finalize(p.sums, n)

@@ -13,24 +13,33 @@ import torch
 from fava_b200 import device, dist
 
 
-def slab_profiles(rho, ux, uy, uz, axis: int, cell_volume: float, layer_volume: float, favre: bool = True,
-                  gather: bool = True) -> dict[str, torch.Tensor]:
-    """Profiles of the global grid formed by stacking the ranks' slabs along z.
+def slab_moments_local(rho, ux, uy, uz, axis: int):
+    """Kernel-only half of `slab_profiles`: this rank's pivoted plane moments (no collective)."""
+    return device.plane_moments(rho, ux, uy, uz, axis)
 
-    Pivots: for axis 0/1 a plane crosses every slab, so all ranks must share one pivot per plane:
-    rank 0's (its slab holds the plane's first cell, z = 0) is broadcast.  For axis 2 every plane
-    lives on one rank and the pivot stays local.
-    """
+
+def slab_profiles_finish(mom, piv, axis: int, cell_volume: float, layer_volume: float, favre: bool = True,
+                         gather: bool = True) -> dict[str, torch.Tensor]:
+    """Collective half: for axis 0/1 a plane crosses every slab, so the ranks first agree on ONE pivot per
+    plane (rank 0's — its slab holds the plane's first cell, z = 0), re-express their moments about it
+    (exact algebra) and add them with one packed [14][N] all-reduce; for axis 2 every plane lives on one
+    rank and the profiles are simply concatenated."""
     if axis in (0, 1):
-        piv = device.plane_pivots(ux, uy, uz, axis)
-        dist.broadcast_(piv, src=0)
-        mom, _ = device.plane_moments(rho, ux, uy, uz, axis, pivots=piv)
-        dist.allreduce_sum_(mom)
+        if dist.world_size() > 1:
+            piv = agree_pivots(mom, piv)
+            dist.allreduce_sum_(mom)
         return device.moments_finalize(mom, piv, cell_volume, layer_volume, favre=favre)
-    out = device.plane_profiles(rho, ux, uy, uz, axis, cell_volume, layer_volume, favre=favre)
+    out = device.moments_finalize(mom, piv, cell_volume, layer_volume, favre=favre)
     if gather and dist.world_size() > 1:
         out = {k: dist.all_gather_cat(v, dim=1) for k, v in out.items()}
     return out
+
+
+def slab_profiles(rho, ux, uy, uz, axis: int, cell_volume: float, layer_volume: float, favre: bool = True,
+                  gather: bool = True) -> dict[str, torch.Tensor]:
+    """Profiles of the global grid formed by stacking the ranks' slabs along z."""
+    mom, piv = slab_moments_local(rho, ux, uy, uz, axis)
+    return slab_profiles_finish(mom, piv, axis, cell_volume, layer_volume, favre=favre, gather=gather)
 
 
 def agree_pivots(mom: torch.Tensor, piv: torch.Tensor) -> torch.Tensor:
@@ -75,3 +84,27 @@ def slab_plane_sum(field, axis: int, cell_volume: float) -> torch.Tensor:
 def block_plane_sum(blocks, axis: int, table, nbins: int) -> torch.Tensor:
     out = device.plane_sum_blocks(blocks, axis, table, nbins)
     return dist.allreduce_sum_(out)
+
+
+def slab_step(rho, ux, uy, uz, n: int, cell_volume: float, layer_volume: float, axes=(0, 1, 2), spectrum: bool = True,
+              favre: bool = True) -> dict:
+    """One full statistics pass over a snapshot held as z-slabs: plane profiles along `axes` plus the
+    kinetic-energy spectrum, scheduled so that the moment kernels (HBM-bound, no communication) run while
+    the spectrum's slab exchange (NVLink-bound) is in flight; the profile collectives follow afterwards so
+    that they never queue behind the exchange fences.  Returns {axis: profile dict, ..., "spectrum": dict}."""
+    from fava_b200 import spectrum as spec
+
+    out, pending = {}, {}
+
+    def local_moments():
+        for ax in axes:
+            pending[ax] = slab_moments_local(rho, ux, uy, uz, ax)
+
+    if spectrum:
+        out["spectrum"] = spec.slab_ke_spectrum(rho, ux, uy, uz, n, overlap=local_moments)
+    else:
+        local_moments()
+    for ax in axes:
+        mom, piv = pending[ax]
+        out[ax] = slab_profiles_finish(mom, piv, ax, cell_volume, layer_volume, favre=favre, gather=False)
+    return out
