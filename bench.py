@@ -323,6 +323,21 @@ def run_ours(args) -> dict:
                                   "achieved_gbs": B_SPECTRUM * local_cells / (spec_ms * 1e-3) / 1e9}
         summary["ke_spectrum"]["frac_of_hbm_peak"] = summary["ke_spectrum"]["achieved_gbs"] / peak
 
+    timeline = None
+    if world > 1 and wl["spectrum"]:  # where one public step spends its time (events on both streams, rank 0)
+        p = spectrum._plan(n, rank, world, dev)
+        s0 = torch.cuda.Event(enable_timing=True)
+        s1 = torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        torch.cuda.synchronize()
+        s0.record()
+        step(fields)
+        s1.record()
+        torch.cuda.synchronize()
+        timeline = {"xy_done_ms": [s0.elapsed_time(e) for e in p.ev_xy], "exchange_done_ms": [s0.elapsed_time(e) for e in p.ev_done],
+                    "moments_done_ms": s0.elapsed_time(p.ev_mark["overlap"]), "fft_z_done_ms": s0.elapsed_time(p.ev_mark["fft_z"]),
+                    "bin_done_ms": s0.elapsed_time(p.ev_mark["bin"]), "step_done_ms": s0.elapsed_time(s1)}
+
     e2e = run_e2e(args, wl, dev, rank, world, fields, step)
 
     out = {
@@ -349,6 +364,7 @@ def run_ours(args) -> dict:
         "roofline": roofline,
         "roofline_stages": stages,
         "roofline_summary": summary,
+        "timeline": timeline,
         "clocks": clocks,
     }
     if rank == 0 and world == 1:

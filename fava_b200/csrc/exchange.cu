@@ -24,7 +24,8 @@ constexpr int kPackUnroll = 16;  // 16 x 16 B per lane = one 8 KB row (N = 1024)
 
 __global__ void __launch_bounds__(kPackThreads)
     k_a2a_pack(const double2* __restrict__ in, double2* const* __restrict__ peer_recv,
-               const int32_t* __restrict__ ky_of_dest, int me, int nranks, int nz_local, int n, int nyl, int nxh) {
+               const int32_t* __restrict__ ky_of_dest, int me, int nranks, int nz_local, int n, int nyl, int nxh,
+               int kmax2) {
     const int lane = threadIdx.x & 31;
     const int64_t total = (int64_t)nz_local * nranks * nyl;
     const int64_t stride = (int64_t)gridDim.x * kPackWarps;
@@ -35,17 +36,23 @@ __global__ void __launch_bounds__(kPackThreads)
         const int dest = (int)((it / ((int64_t)nyl * nz_local) + me) % nranks);
         const int j = ky_of_dest[dest * nyl + jl];
         if (j < 0) continue;
+        // columns with kx^2 + ky^2 beyond the last shell can never reach a bin, whatever kz: not sent
+        // (21 % of the NVLink bytes; the receive buffers are zero there from their allocation)
+        const int ky = j < n / 2 ? j : j - n;
+        const int rem = kmax2 - ky * ky;
+        if (rem < 0) continue;
+        const int nsend = min(nxh, (int)sqrt((double)rem) + 2);
         const double2* src = in + ((int64_t)zl * n + j) * nxh;
         double2* dst = peer_recv[dest] + (((int64_t)me * nz_local + zl) * nyl + jl) * nxh;
         int x = lane;
-        for (; x + (kPackUnroll - 1) * 32 < nxh; x += kPackUnroll * 32) {
+        for (; x + (kPackUnroll - 1) * 32 < nsend; x += kPackUnroll * 32) {
             double2 v[kPackUnroll];
 #pragma unroll
             for (int u = 0; u < kPackUnroll; ++u) v[u] = __ldcs(src + x + u * 32);
 #pragma unroll
             for (int u = 0; u < kPackUnroll; ++u) dst[x + u * 32] = v[u];
         }
-        for (; x < nxh; x += 32) dst[x] = __ldcs(src + x);
+        for (; x < nsend; x += 32) dst[x] = __ldcs(src + x);
     }
 }
 
@@ -66,11 +73,11 @@ int fava_a2a_pack(fava_ctx* ctx, const double* d_in, double* const* d_peer_recv,
         const char* e = getenv("FAVA_A2A_CTAS");
         return e ? atoi(e) : 0;
     }();
-    const int want = env_ctas > 0 ? env_ctas : 48;
+    const int want = env_ctas > 0 ? env_ctas : 64;
     const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(total, want));
     k_a2a_pack<<<gx, kPackThreads, 0, (cudaStream_t)stream>>>((const double2*)d_in, (double2* const*)d_peer_recv,
                                                               d_ky_of_dest, my_rank, nranks, (int)nz_local, (int)n,
-                                                              (int)nyl, (int)(n / 2 + 1));
+                                                              (int)nyl, (int)(n / 2 + 1), (int)(n * n / 4 - 3 * n / 2 + 2));
     FAVA_LAUNCHED();
     return FAVA_OK;
 }

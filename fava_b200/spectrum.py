@@ -77,8 +77,20 @@ class SlabPlan:
         self.sums = torch.zeros((3, n // 2 - 1), dtype=torch.float64, device=dev)
         self.tokens = [torch.zeros(1, dtype=torch.float32, device=dev) for _ in range(3)]
         self.comm_stream = torch.cuda.Stream(device=dev, priority=-1)  # NVLink exchange runs beside the HBM-bound kernels
-        self.ev_xy = [torch.cuda.Event() for _ in range(3)]
-        self.ev_done = [torch.cuda.Event() for _ in range(3)]
+        self.ev_xy = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        self.ev_done = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        self.ev_mark = {k: torch.cuda.Event(enable_timing=True) for k in ("overlap", "fft_z", "bin")}
+        dist.barrier()
+
+
+    def close(self) -> None:
+        """Unmap the peers' buffers (collective: every rank drops the plan at the same point)."""
+        torch.cuda.synchronize(self.dev)
+        dist.barrier()
+        lib = device._lib.load()
+        for p in self._opened:
+            lib.fava_ipc_close(device.C.c_void_p(p))
+        self._opened = []
         dist.barrier()
 
 
@@ -86,23 +98,30 @@ _plans: dict = {}
 
 
 def _plan(n: int, rank: int, world: int, dev) -> SlabPlan:
+    """One live plan at a time: the exchange buffers are grow-only context workspaces, so a plan for another
+    grid size may re-allocate them and would leave the peers' mappings of the old buffers dangling."""
     key = (n, rank, world, str(dev))
     if key not in _plans:
+        for old in _plans.values():
+            old.close()
+        _plans.clear()
         _plans[key] = SlabPlan(n, rank, world, dev)
     return _plans[key]
 
 
-def slab_ke_spectrum(rho, ux, uy, uz, n: int, overlap=None) -> dict[str, np.ndarray]:
+def slab_ke_spectrum(rho, ux, uy, uz, n: int, overlap=None, epilogue=None) -> dict[str, np.ndarray]:
     """Spectrum of the global N^3 grid formed by the ranks' z-slabs; every rank returns the full dict.
 
     Schedule: the exchange of component c (K5, NVLink-bound, on a side stream) overlaps the 2-D transforms
     of component c+1 and whatever `overlap()` enqueues on the calling stream (bench.py and
     stats.slab_step put the HBM-bound plane-profile kernels there); the z-transform of component c
-    starts as soon as ITS exchange has completed on every rank."""
+    starts as soon as ITS exchange has completed on every rank.  `epilogue()` is enqueued after the binning
+    kernel and before the host synchronises on the shell sums."""
     world, rank = dist.world_size(), dist.rank()
     if world == 1:
-        if overlap is not None:
-            overlap()
+        for hook in (overlap, epilogue):
+            if hook is not None:
+                hook()
         return device.ke_spectrum(rho, ux, uy, uz)
     nzl = int(rho.shape[0])
     if nzl * world != n or tuple(rho.shape[1:]) != (n, n):
@@ -123,11 +142,16 @@ def slab_ke_spectrum(rho, ux, uy, uz, n: int, overlap=None) -> dict[str, np.ndar
             p.ev_done[c].record(p.comm_stream)
     if overlap is not None:
         overlap()
+    p.ev_mark["overlap"].record(cur)
     for c in range(3):
         cur.wait_event(p.ev_done[c])
         device.fft_z(p.recv[c], n, p.nyl * p.nxh, dev)
+    p.ev_mark["fft_z"].record(cur)
     device.spectrum_bin(p.recv[0], p.recv[1], p.recv[2], n, p.nyl, p.ky_of_local, p.local_of_ky, p.sums)
     # shell sums and counts add across ranks; this collective also fences the receive buffers against
     # the next call's remote stores (a rank's next pack is stream-ordered after it)
+    p.ev_mark["bin"].record(cur)
     dist.allreduce_sum_(p.sums)
+    if epilogue is not None:  # enqueued before the host waits for the shell sums
+        epilogue()
     return device.spectrum_finalize(p.sums, n)

@@ -100,11 +100,14 @@ def slab_step(rho, ux, uy, uz, n: int, cell_volume: float, layer_volume: float, 
         for ax in axes:
             pending[ax] = slab_moments_local(rho, ux, uy, uz, ax)
 
+    def finish_profiles():
+        for ax in axes:
+            mom, piv = pending[ax]
+            out[ax] = slab_profiles_finish(mom, piv, ax, cell_volume, layer_volume, favre=favre, gather=False)
+
     if spectrum:
-        out["spectrum"] = spec.slab_ke_spectrum(rho, ux, uy, uz, n, overlap=local_moments)
+        out["spectrum"] = spec.slab_ke_spectrum(rho, ux, uy, uz, n, overlap=local_moments, epilogue=finish_profiles)
     else:
         local_moments()
-    for ax in axes:
-        mom, piv = pending[ax]
-        out[ax] = slab_profiles_finish(mom, piv, ax, cell_volume, layer_volume, favre=favre, gather=False)
+        finish_profiles()
     return out

@@ -51,6 +51,23 @@ def main():
         for k in one:
             close(many[k], one[k], 1e-13, f"slab spectrum {k} (call {rep})")
 
+    # a different grid size in the same process: the plan (buffers, peer mappings) is replaced collectively
+    n2 = n // 2
+    full2 = synth.uniform_fields((n2, n2, n2), names=("dens", "velx", "vely", "velz"), seed=77)
+    tf2 = [torch.from_numpy(full2[k].copy()).to(dev) for k in ("dens", "velx", "vely", "velz")]
+    a2, b2 = dist.parallel_range(n2)
+    one2 = device.ke_spectrum(*tf2)
+    many2 = spectrum.slab_ke_spectrum(*[t[a2:b2].contiguous() for t in tf2], n2)
+    for k in one2:
+        close(many2[k], one2[k], 1e-13, f"slab spectrum {k} (second grid size)")
+    step = stats.slab_step(*ts, n, cv, lv)
+    for k in one:
+        close(step["spectrum"][k], one[k], 1e-13, f"slab_step spectrum {k}")
+    for axis in (0, 1):
+        ref_ax = device.plane_profiles(*tf, axis, cv, lv)
+        for k in ref_ax:
+            close(step[axis][k].cpu().numpy(), ref_ax[k].cpu().numpy(), 1e-13, f"slab_step profiles {k} axis {axis}")
+
     # --- block datasets: contiguous block ranges per rank, file -> staging -> kernels
     tmp = Path(tempfile.gettempdir()) / f"fava_mgpu_{os.environ.get('MASTER_PORT', '0')}"
     if rank == 0:
