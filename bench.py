@@ -231,7 +231,7 @@ def run_ours(args) -> dict:
                 with timer.bracket("cufft_xy"):
                     device.fft_xy(p.send[c], p.nzl, n, n, dev)
                 with timer.bracket("a2a_pack"):
-                    device.a2a_pack(p.send[c], p.peer_tables[c], p.ky_of_dest, rank, world, p.nzl, n, p.nyl)
+                    spectrum.exchange(p, c)
             dist.allreduce_sum_(p.tokens[0])
             for c in range(3):
                 with timer.bracket("cufft_z"):

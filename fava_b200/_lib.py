@@ -97,6 +97,10 @@ SIGNATURES: dict[str, tuple] = {
         c_int,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_i64, c_i64, c_i64, c_void_p],
     ),
+    "fava_a2a_copy": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_i64, c_i64, c_i64, c_void_p],
+    ),
     "fava_spectrum_bin": (
         c_int,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_void_p, c_double, c_void_p, c_void_p],

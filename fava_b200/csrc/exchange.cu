@@ -18,8 +18,7 @@ namespace fava {
 // Persistent form: a SMALL grid (default 48 CTAs, FAVA_A2A_CTAS) walks all rows, so the kernel occupies only a
 // fraction of the SMs and — launched on a high-priority side stream — runs BESIDE the HBM-bound FFT / moment
 // kernels instead of queueing behind them; NVLink (~0.6 TB/s) needs far fewer SMs than HBM does.
-constexpr int kPackThreads = 512;
-constexpr int kPackWarps = kPackThreads / 32;
+constexpr int kPackThreads = 512;  // upper bound; the launch may use fewer (FAVA_A2A_THREADS)
 constexpr int kPackUnroll = 16;  // 16 x 16 B per lane = one 8 KB row (N = 1024) per warp in flight
 
 __global__ void __launch_bounds__(kPackThreads)
@@ -28,12 +27,14 @@ __global__ void __launch_bounds__(kPackThreads)
                int kmax2) {
     const int lane = threadIdx.x & 31;
     const int64_t total = (int64_t)nz_local * nranks * nyl;
-    const int64_t stride = (int64_t)gridDim.x * kPackWarps;
-    // one warp per ky row; destination-major order staggered by rank: at any time the ranks write to different peers
-    for (int64_t it = (int64_t)blockIdx.x * kPackWarps + (threadIdx.x >> 5); it < total; it += stride) {
+    const int nwarps = blockDim.x >> 5;
+    const int64_t stride = (int64_t)gridDim.x * nwarps;
+    // one warp per ky row; consecutive row groups go to different peers (staggered by rank), so every NVLink
+    // port of the switch is busy at any time
+    for (int64_t it = (int64_t)blockIdx.x * nwarps + (threadIdx.x >> 5); it < total; it += stride) {
         const int jl = (int)(it % nyl);
-        const int zl = (int)((it / nyl) % nz_local);
-        const int dest = (int)((it / ((int64_t)nyl * nz_local) + me) % nranks);
+        const int dest = (int)(((it / nyl) % nranks + me) % nranks);
+        const int zl = (int)(it / ((int64_t)nyl * nranks));
         const int j = ky_of_dest[dest * nyl + jl];
         if (j < 0) continue;
         // columns with kx^2 + ky^2 beyond the last shell can never reach a bin, whatever kz: not sent
@@ -56,6 +57,123 @@ __global__ void __launch_bounds__(kPackThreads)
     }
 }
 
+
+// ---- TMA form: bulk asynchronous copies, one elected thread per CTA ---------------------------------------
+// global -> shared (cp.async.bulk, completion on an mbarrier) -> peer global (cp.async.bulk store over NVLink).
+// No registers or LSU slots are spent on the payload, so a handful of 32-thread CTAs keeps megabytes in
+// flight while the HBM-bound kernels of the other stream own the SMs.  Ring of kSlots row buffers: row i is
+// loaded kAhead iterations before it is stored; a slot is refilled once the store issued kSlots-kAhead
+// iterations earlier has finished READING it (bulk-group completion is in order).
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+}
+
+constexpr int kTmaSlots = 12;
+constexpr int kTmaAhead = 8;  // loads in flight; kTmaSlots - kTmaAhead stores may still be reading their slot
+
+struct PackRow {
+    const double2* src;
+    double2* dst;
+    unsigned bytes;
+};
+
+__device__ __forceinline__ bool pack_row(int64_t it, const double2* in, double2* const* peer_recv,
+                                         const int32_t* ky_of_dest, int me, int nranks, int nz_local, int n, int nyl,
+                                         int nxh, int kmax2, PackRow* r) {
+    const int jl = (int)(it % nyl);
+    const int dest = (int)(((it / nyl) % nranks + me) % nranks);
+    const int zl = (int)(it / ((int64_t)nyl * nranks));
+    const int j = ky_of_dest[dest * nyl + jl];
+    if (j < 0) return false;
+    const int ky = j < n / 2 ? j : j - n;
+    const int rem = kmax2 - ky * ky;
+    if (rem < 0) return false;
+    const int nsend = min(nxh, (int)sqrt((double)rem) + 2);
+    r->src = in + ((int64_t)zl * n + j) * nxh;
+    r->dst = peer_recv[dest] + (((int64_t)me * nz_local + zl) * nyl + jl) * nxh;
+    r->bytes = (unsigned)nsend * 16u;
+    return true;
+}
+
+__global__ void __launch_bounds__(32)
+    k_a2a_pack_tma(const double2* __restrict__ in, double2* const* __restrict__ peer_recv,
+                   const int32_t* __restrict__ ky_of_dest, int me, int nranks, int nz_local, int n, int nyl, int nxh,
+                   int kmax2) {
+    extern __shared__ __align__(128) unsigned char ring[];  // kTmaSlots x slot_bytes
+    __shared__ __align__(8) uint64_t bars[kTmaSlots];
+    if (threadIdx.x != 0) return;
+    const unsigned slot_bytes = ((unsigned)nxh * 16u + 127u) & ~127u;
+    for (int s = 0; s < kTmaSlots; ++s) mbar_init(&bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async;\n" ::: "memory");
+
+    const int64_t total = (int64_t)nz_local * nranks * nyl;
+    int64_t it_load = blockIdx.x;  // next work item to consider for loading
+    // rows are numbered in issue order; row q lives in slot q % kTmaSlots and uses that slot's barrier with
+    // parity (q / kTmaSlots) & 1
+    int64_t q_load = 0, q_store = 0;
+    PackRow rows[kTmaSlots];
+
+    auto issue_load = [&]() -> bool {
+        PackRow r;
+        while (it_load < total) {
+            const bool ok = pack_row(it_load, in, peer_recv, ky_of_dest, me, nranks, nz_local, n, nyl, nxh, kmax2, &r);
+            it_load += gridDim.x;
+            if (ok) {
+                const int s = (int)(q_load % kTmaSlots);
+                rows[s] = r;
+                mbar_expect_tx(&bars[s], r.bytes);
+                bulk_load(ring + (size_t)s * slot_bytes, r.src, r.bytes, &bars[s]);
+                ++q_load;
+                return true;
+            }
+        }
+        return false;
+    };
+
+    for (int k = 0; k < kTmaAhead; ++k)
+        if (!issue_load()) break;
+    while (q_store < q_load) {
+        const int s = (int)(q_store % kTmaSlots);
+        mbar_wait(&bars[s], (unsigned)((q_store / kTmaSlots) & 1));
+        bulk_store(rows[s].dst, ring + (size_t)s * slot_bytes, rows[s].bytes);
+        asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+        ++q_store;
+        // the slot about to be refilled (row q_load) was last stored as row q_load - kTmaSlots: at most
+        // kTmaSlots - kTmaAhead - 1 newer store groups may remain pending
+        asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(kTmaSlots - kTmaAhead - 1) : "memory");
+        issue_load();
+    }
+    asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+    __threadfence_system();
+}
+
 }  // namespace fava
 
 using namespace fava;
@@ -69,16 +187,62 @@ int fava_a2a_pack(fava_ctx* ctx, const double* d_in, double* const* d_peer_recv,
     FAVA_REQUIRE(nz_local > 0 && n > 1 && (n & 1) == 0 && nyl > 0, "fava_a2a_pack: bad shape");
     DeviceGuard g(ctx->device);
     const int64_t total = nz_local * nranks * nyl;
-    static const int env_ctas = [] {
-        const char* e = getenv("FAVA_A2A_CTAS");
-        return e ? atoi(e) : 0;
-    }();
-    const int want = env_ctas > 0 ? env_ctas : 64;
+    const char* e_ctas = getenv("FAVA_A2A_CTAS");  // tuning knobs, read per call
+    const int env_ctas = e_ctas ? atoi(e_ctas) : 0;
+    const char* e_thr = getenv("FAVA_A2A_THREADS");
+    const int env_thr = e_thr ? std::max(32, std::min(kPackThreads, atoi(e_thr) / 32 * 32)) : 0;
+    const char* e_mode = getenv("FAVA_A2A_MODE");  // "ldst" selects the load/store kernel; default: bulk-copy (TMA) kernel
+    const int env_mode = (e_mode && e_mode[0] == 'l') ? 1 : 0;
+    const int kmax2 = (int)(n * n / 4 - 3 * n / 2 + 2);
+    const size_t slot_bytes = ((size_t)(n / 2 + 1) * 16 + 127) & ~size_t(127);
+    const size_t ring_bytes = slot_bytes * kTmaSlots;
+    if (env_mode == 0 && ring_bytes <= 200 * 1024) {
+        const int want = env_ctas > 0 ? env_ctas : 64;
+        const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(total, want));
+        FAVA_CHECK_CUDA(cudaFuncSetAttribute(k_a2a_pack_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes));
+        k_a2a_pack_tma<<<gx, 32, ring_bytes, (cudaStream_t)stream>>>((const double2*)d_in, (double2* const*)d_peer_recv,
+                                                                     d_ky_of_dest, my_rank, nranks, (int)nz_local, (int)n,
+                                                                     (int)nyl, (int)(n / 2 + 1), kmax2);
+        FAVA_LAUNCHED();
+        return FAVA_OK;
+    }
+    const int want = env_ctas > 0 ? env_ctas : 2 * ctx->num_sms;
+    const int threads = env_thr > 0 ? env_thr : 128;
     const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(total, want));
-    k_a2a_pack<<<gx, kPackThreads, 0, (cudaStream_t)stream>>>((const double2*)d_in, (double2* const*)d_peer_recv,
+    k_a2a_pack<<<gx, threads, 0, (cudaStream_t)stream>>>((const double2*)d_in, (double2* const*)d_peer_recv,
                                                               d_ky_of_dest, my_rank, nranks, (int)nz_local, (int)n,
                                                               (int)nyl, (int)(n / 2 + 1), (int)(n * n / 4 - 3 * n / 2 + 2));
     FAVA_LAUNCHED();
+    return FAVA_OK;
+}
+
+int fava_a2a_copy(fava_ctx* ctx, const double* d_in, double* const* h_peer_recv, const int32_t* h_ky_of_dest,
+                  int my_rank, int nranks, int64_t nz_local, int64_t n, int64_t nyl, void* stream) {
+    FAVA_REQUIRE(ctx && d_in && h_peer_recv && h_ky_of_dest, "fava_a2a_copy: NULL argument");
+    FAVA_REQUIRE(nranks > 0 && my_rank >= 0 && my_rank < nranks, "fava_a2a_copy: bad rank %d of %d", my_rank, nranks);
+    FAVA_REQUIRE(nz_local > 0 && n > 1 && (n & 1) == 0 && nyl > 0, "fava_a2a_copy: bad shape");
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t nxh = n / 2 + 1;
+    const size_t row = (size_t)nxh * 16;
+    for (int k = 1; k <= nranks; ++k) {  // staggered: at any time the ranks target different peers
+        const int dest = (my_rank + k) % nranks;
+        const int32_t* own = h_ky_of_dest + (int64_t)dest * nyl;
+        int64_t jl = 0;
+        while (jl < nyl) {
+            if (own[jl] < 0) {
+                ++jl;
+                continue;
+            }
+            int64_t len = 1;  // run of consecutive ky rows: contiguous in the source AND in the destination
+            while (jl + len < nyl && own[jl + len] == own[jl] + len) ++len;
+            const char* src = (const char*)d_in + (size_t)own[jl] * row;
+            char* dst = (char*)h_peer_recv[dest] + ((size_t)my_rank * nz_local * nyl + jl) * row;
+            FAVA_CHECK_CUDA(cudaMemcpy2DAsync(dst, (size_t)nyl * row, src, (size_t)n * row, (size_t)len * row,
+                                              (size_t)nz_local, cudaMemcpyDefault, st));
+            jl += len;
+        }
+    }
     return FAVA_OK;
 }
 

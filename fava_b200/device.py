@@ -382,6 +382,15 @@ def a2a_pack(src: int, peer_table: torch.Tensor, ky_of_dest: torch.Tensor, rank:
                                      nz_local, n, nyl, _stream(peer_table)), "fava_a2a_pack")
 
 
+def a2a_copy(src: int, peer_ptrs: np.ndarray, ky_of_dest: np.ndarray, rank: int, world: int, nz_local: int, n: int,
+             nyl: int, dev) -> None:
+    """Copy-engine form of the exchange (fava_a2a_copy); peer_ptrs uint64[world], ky_of_dest int32[world][nyl] on the host."""
+    ctx = get_context(dev)
+    _lib.check(ctx.lib.fava_a2a_copy(ctx.handle, C.c_void_p(src), C.c_void_p(peer_ptrs.ctypes.data),
+                                     C.c_void_p(ky_of_dest.ctypes.data), rank, world, nz_local, n, nyl, _cur_stream(dev)),
+               "fava_a2a_copy")
+
+
 def spectrum_bin(fx: int, fy: int, fz: int, n: int, ny_local: int, ky_of_local, local_of_ky, sums: torch.Tensor) -> None:
     ctx = get_context(sums.device)
     norm = 1.0 / (float(n) ** 3)

@@ -11,6 +11,8 @@ u^(kz, +-ky, kx) the reference's `.T` projection needs (FlashUniform.py:281) is 
 
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -49,6 +51,7 @@ class SlabPlan:
         own = ky_ownership(n, world)
         self.nyl = own.shape[1]
         self.ky_of_dest = torch.from_numpy(own).to(dev)
+        self.ky_of_dest_host = np.ascontiguousarray(own, dtype=np.int32)
         mine = own[rank]
         inv = -np.ones(n, dtype=np.int32)
         inv[mine[mine >= 0]] = np.flatnonzero(mine >= 0).astype(np.int32)
@@ -63,6 +66,7 @@ class SlabPlan:
         gathered = [None] * world
         torch.distributed.all_gather_object(gathered, handles)
         self.peer_tables = []
+        self.peer_ptrs_host = []
         self._opened = []
         for c in range(3):
             ptrs = []
@@ -74,6 +78,7 @@ class SlabPlan:
                     self._opened.append(p)
                     ptrs.append(p)
             self.peer_tables.append(torch.tensor(ptrs, dtype=torch.int64, device=dev))
+            self.peer_ptrs_host.append(np.array(ptrs, dtype=np.uint64))
         self.sums = torch.zeros((3, n // 2 - 1), dtype=torch.float64, device=dev)
         self.tokens = [torch.zeros(1, dtype=torch.float32, device=dev) for _ in range(3)]
         self.comm_stream = torch.cuda.Stream(device=dev, priority=-1)  # NVLink exchange runs beside the HBM-bound kernels
@@ -109,6 +114,20 @@ def _plan(n: int, rank: int, world: int, dev) -> SlabPlan:
     return _plans[key]
 
 
+def exchange(p: SlabPlan, c: int) -> None:
+    """Slab -> ky-pencil exchange of component c on the current stream.  FAVA_A2A_MODE selects the engine:
+    "tma" (default) = the fused pack kernel K5 on cp.async.bulk: 64 single-warp CTAs stream ky rows
+    global -> shared -> the owner's peer-mapped buffer and skip the columns outside the spectral disc
+    (measured at 8 GPUs, 1024^3: 1.37 ms per component, 685 GB/s of algorithmic bytes per GPU);
+    "ldst" = the same kernel with 16-byte loads/stores from registers (1.68 ms); "ce" = strided 2-D peer
+    copies on the copy engines (no SM use, no pruning, 1.59 ms)."""
+    mode = os.environ.get("FAVA_A2A_MODE", "tma")
+    if mode == "ce":
+        device.a2a_copy(p.send[c], p.peer_ptrs_host[c], p.ky_of_dest_host, p.rank, p.world, p.nzl, p.n, p.nyl, p.dev)
+    else:
+        device.a2a_pack(p.send[c], p.peer_tables[c], p.ky_of_dest, p.rank, p.world, p.nzl, p.n, p.nyl)
+
+
 def slab_ke_spectrum(rho, ux, uy, uz, n: int, overlap=None, epilogue=None) -> dict[str, np.ndarray]:
     """Spectrum of the global N^3 grid formed by the ranks' z-slabs; every rank returns the full dict.
 
@@ -135,7 +154,7 @@ def slab_ke_spectrum(rho, ux, uy, uz, n: int, overlap=None, epilogue=None) -> di
         p.ev_xy[c].record(cur)
         with torch.cuda.stream(p.comm_stream):
             p.comm_stream.wait_event(p.ev_xy[c])
-            device.a2a_pack(p.send[c], p.peer_tables[c], p.ky_of_dest, rank, world, p.nzl, n, p.nyl)
+            exchange(p, c)
             # every rank's stores of component c into my receive buffer are complete once all ranks have
             # passed this stream-ordered collective (each enqueues it after its own pack kernel)
             dist.allreduce_sum_(p.tokens[c])

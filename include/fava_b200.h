@@ -181,6 +181,12 @@ int fava_fft_z(fava_ctx* ctx, double* d_data, int64_t nz, int64_t rows, void* st
  * NVLink stores overlap the gather. */
 int fava_a2a_pack(fava_ctx* ctx, const double* d_in, double* const* d_peer_recv, const int32_t* d_ky_of_dest,
                   int my_rank, int nranks, int64_t nz_local, int64_t n, int64_t nyl, void* stream);
+/* The same exchange on the copy engines: per destination the owned ky rows form (at most two) contiguous
+ * runs, so the whole exchange is a handful of strided 2-D peer copies (one cudaMemcpy2DAsync per run) that
+ * use no SM at all and overlap the HBM-bound kernels completely.  h_peer_recv / h_ky_of_dest are HOST arrays
+ * (nranks device pointers; [nranks][nyl] ky indices). */
+int fava_a2a_copy(fava_ctx* ctx, const double* d_in, double* const* h_peer_recv, const int32_t* h_ky_of_dest,
+                  int my_rank, int nranks, int64_t nz_local, int64_t n, int64_t nyl, void* stream);
 /* Shell binning of one spectral sub-volume complex [n (kz)][ny_local][n/2+1] x 3 components of an n^3
  * transform scaled by `norm` (1/n^3, norm="forward").  Row jl holds global ky index d_ky_of_local[jl];
  * d_local_of_ky[n] is the inverse (-1 = not held); both NULL = this GPU holds every ky in order.
