@@ -91,6 +91,12 @@ SIGNATURES: dict[str, tuple] = {
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_i64, c_i64, c_void_p, c_void_p, c_void_p,
          c_void_p],
     ),
+    "fava_fft_native_supported": (c_int, [c_i64]),
+    "fava_fft_x_weight3": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_i64, c_void_p, c_void_p, c_void_p, c_void_p],
+    ),
+    "fava_fft_cols": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_void_p, c_void_p]),
     "fava_fft_xy": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p]),
     "fava_fft_z": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_void_p]),
     "fava_a2a_pack": (

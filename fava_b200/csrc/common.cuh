@@ -64,6 +64,7 @@ struct fava_ctx {
     // cuFFT plans keyed by (kind, a, b, c)
     std::map<std::tuple<int, int64_t, int64_t, int64_t>, cufftHandle> plans;
     std::map<std::tuple<int, int64_t, int64_t, int64_t>, size_t> plan_work;  // work-area bytes per plan
+    std::map<int64_t, void*> twiddles;  // exp(-2 pi i m / N) tables of the native FFT, per N
     fava::Staging* staging = nullptr;
 };
 
@@ -71,6 +72,9 @@ namespace fava {
 
 // Grow-only device workspace owned by the context.
 int ctx_workspace(fava_ctx* ctx, int slot, size_t bytes, void** out);
+
+// native (hand-written) FFT available for this grid size?  (power of two in [64, 4096], not FAVA_FFT=cufft)
+bool fft_native_supported(int64_t n);
 
 struct DeviceGuard {
     int prev = -1;

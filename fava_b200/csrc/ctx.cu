@@ -88,6 +88,7 @@ int fava_shutdown(fava_ctx* ctx) {
     cudaDeviceSynchronize();
     if (ctx->staging) staging_destroy(ctx->staging);
     for (auto& kv : ctx->plans) cufftDestroy(kv.second);
+    for (auto& kv : ctx->twiddles) cudaFree(kv.second);
     for (int i = 0; i < WS_COUNT; ++i)
         if (ctx->ws[i]) cudaFree(ctx->ws[i]);
     delete ctx;

@@ -427,14 +427,29 @@ int fava_ke_spectrum(fava_ctx* ctx, const void* d_rho, const void* d_ux, const v
     void* sums;
     rc = ctx_workspace(ctx, WS_AUX, sizeof(double) * 3 * (size_t)(n / 2 - 1), &sums);
     if (rc) return rc;
-    rc = fava_ke_weight3(ctx, d_rho, d_ux, d_uy, d_uz, dtype, n * n, n, 2 * nxh, (double*)w[0], (double*)w[1],
-                         (double*)w[2], stream);
-    if (rc) return rc;
-    for (int c = 0; c < 3; ++c) {
-        rc = fava_fft_xy(ctx, (double*)w[c], n, n, n, stream);
+    if (fft_native_supported(n)) {
+        // hand-written path: weighting fused into the x pass, strided y pass, disc-pruned z pass (csrc/fft.cu)
+        rc = fava_fft_x_weight3(ctx, d_rho, d_ux, d_uy, d_uz, dtype, n * n, n, (double*)w[0], (double*)w[1],
+                                (double*)w[2], stream);
         if (rc) return rc;
-        rc = fava_fft_z(ctx, (double*)w[c], n, n * nxh, stream);
+        for (int c = 0; c < 3; ++c) {
+            rc = fava_fft_cols(ctx, (double*)w[c], n, nxh, n, 0, nullptr, stream);
+            if (rc) return rc;
+        }
+        for (int c = 0; c < 3; ++c) {
+            rc = fava_fft_cols(ctx, (double*)w[c], n, n * nxh, 1, n, nullptr, stream);
+            if (rc) return rc;
+        }
+    } else {
+        rc = fava_ke_weight3(ctx, d_rho, d_ux, d_uy, d_uz, dtype, n * n, n, 2 * nxh, (double*)w[0], (double*)w[1],
+                             (double*)w[2], stream);
         if (rc) return rc;
+        for (int c = 0; c < 3; ++c) {
+            rc = fava_fft_xy(ctx, (double*)w[c], n, n, n, stream);
+            if (rc) return rc;
+            rc = fava_fft_z(ctx, (double*)w[c], n, n * nxh, stream);
+            if (rc) return rc;
+        }
     }
     const double norm = 1.0 / ((double)n * (double)n * (double)n);  // norm="forward" (FlashUniform.py:268)
     rc = fava_spectrum_bin(ctx, (const double*)w[0], (const double*)w[1], (const double*)w[2], n, n, nullptr, nullptr,

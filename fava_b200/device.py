@@ -406,3 +406,23 @@ def spectrum_finalize(sums: torch.Tensor, n: int) -> dict[str, np.ndarray]:
     ptrs = [b.ctypes.data_as(_lib.c_double_p) for b in bufs]
     _lib.check(ctx.lib.fava_spectrum_finalize(ctx.handle, _ptr(sums), n, *ptrs, _stream(sums)), "fava_spectrum_finalize")
     return dict(zip(SPECTRUM_KEYS, bufs))
+
+
+def fft_native_supported(n: int) -> bool:
+    return bool(_lib.load().fava_fft_native_supported(int(n)))
+
+
+def fft_x_weight3(rho, ux, uy, uz, fx: int, fy: int, fz: int) -> None:
+    """x pass fused with the weighting (fava_fft_x_weight3): out complex [nz*ny][nx/2+1] per component."""
+    nz, ny, nx = _check_fields(rho, ux, uy, uz)
+    ctx = get_context(rho.device)
+    _lib.check(ctx.lib.fava_fft_x_weight3(ctx.handle, _ptr(rho), _ptr(ux), _ptr(uy), _ptr(uz), _dtype_code(rho), nz * ny, nx,
+                                          C.c_void_p(fx), C.c_void_p(fy), C.c_void_p(fz), _stream(rho)),
+               "fava_fft_x_weight3")
+
+
+def fft_cols(data: int, n: int, ncols: int, nbatch: int, dev, prune_grid_n: int = 0, ky_of_local=None) -> None:
+    """In-place strided column FFT (fava_fft_cols) of complex [nbatch][n][ncols]."""
+    ctx = get_context(dev)
+    _lib.check(ctx.lib.fava_fft_cols(ctx.handle, C.c_void_p(data), n, ncols, nbatch, int(prune_grid_n),
+                                     _ptr(ky_of_local), _cur_stream(dev)), "fava_fft_cols")

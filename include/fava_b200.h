@@ -167,6 +167,19 @@ int fava_ke_spectrum(fava_ctx* ctx, const void* d_rho, const void* d_ux, const v
 int fava_ke_weight3(fava_ctx* ctx, const void* d_rho, const void* d_ux, const void* d_uy, const void* d_uz,
                     int dtype, int64_t nrows, int64_t nx, int64_t pitch, double* d_wx, double* d_wy,
                     double* d_wz, void* stream);
+/* Hand-written line FFTs (csrc/fft.cu) for power-of-two N in [64, 4096]; 1 if this grid size takes them
+ * (0 => the cuFFT entry points below are used; FAVA_FFT=cufft forces that). */
+int fava_fft_native_supported(int64_t n);
+/* x pass fused with the weighting: reads `nrows` rows of nx cells of rho,ux,uy,uz once and writes, per
+ * component, the Hermitian half spectrum of sqrt(rho)*u along x: complex [nrows][nx/2+1] (FlashUniform.py:266-268). */
+int fava_fft_x_weight3(fava_ctx* ctx, const void* d_rho, const void* d_ux, const void* d_uy, const void* d_uz,
+                       int dtype, int64_t nrows, int64_t nx, double* d_fx, double* d_fy, double* d_fz, void* stream);
+/* In-place complex FFT of length n along the middle axis of complex [nbatch][n][ncols] (y pass: ncols = nx/2+1,
+ * nbatch = local z planes; z pass: ncols = ky rows x (nx/2+1), nbatch = 1).  prune_grid_n > 0 (z pass) skips
+ * column tiles lying outside the spectral disc kx^2 + ky^2 <= (N/2-1.5)^2 of an N = prune_grid_n grid, the
+ * columns being (ky row, kx) pairs with global ky index d_ky_of_local[row] (NULL = identity). */
+int fava_fft_cols(fava_ctx* ctx, double* d_data, int64_t n, int64_t ncols, int64_t nbatch, int64_t prune_grid_n,
+                  const int32_t* d_ky_of_local, void* stream);
 /* In-place batched 2-D FFT (cuFFT D2Z) of a slab: real [nz_local][ny][2*(nx/2+1)] (padded rows) ->
  * complex [nz_local][ny][nx/2+1] (interleaved re,im), transformed along x (halved) and y. */
 int fava_fft_xy(fava_ctx* ctx, double* d_data, int64_t nz_local, int64_t ny, int64_t nx, void* stream);
