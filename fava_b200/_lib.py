@@ -98,6 +98,10 @@ SIGNATURES: dict[str, tuple] = {
     ),
     "fava_fft_cols": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_void_p, c_void_p]),
     "fava_fft_xy": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p]),
+    "fava_ke_weight_fft_xy": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_i64, c_void_p, c_void_p, c_void_p, c_void_p],
+    ),
     "fava_fft_z": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_void_p]),
     "fava_a2a_pack": (
         c_int,

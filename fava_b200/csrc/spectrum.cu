@@ -27,6 +27,7 @@
 // tails add into warp-private tile bins (plain stores), the CTA merges its warps in a fixed order,
 // CTAs own a fixed tile sequence, and k_spectrum_reduce sums CTA partials in index order.
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -346,6 +347,44 @@ int fava_fft_z(fava_ctx* ctx, double* d_data, int64_t nz, int64_t rows, void* st
     return exec_plan(ctx, PLAN_Z, nz, rows, 0, d_data, (cudaStream_t)stream);
 }
 
+int fava_ke_weight_fft_xy(fava_ctx* ctx, const void* d_rho, const void* d_ux, const void* d_uy, const void* d_uz,
+                          int dtype, int64_t nz_local, int64_t n, double* d_wx, double* d_wy, double* d_wz,
+                          void* stream) {
+    FAVA_REQUIRE(ctx && d_rho && d_ux && d_uy && d_uz && d_wx && d_wy && d_wz, "fava_ke_weight_fft_xy: NULL argument");
+    FAVA_REQUIRE(nz_local > 0, "fava_ke_weight_fft_xy: empty slab");
+    FAVA_REQUIRE(dtype == FAVA_F32 || dtype == FAVA_F64, "fava_ke_weight_fft_xy: bad dtype %d", dtype);
+    int rc = check_cube(n, "fava_ke_weight_fft_xy");
+    if (rc) return rc;
+    // Optional plane groups (FAVA_XY_GROUP = z-planes per group): K4 and the two sub-passes of the 2-D transform
+    // run back to back on a few planes at a time, hoping to keep the weighted planes in the 126 MB L2.  Measured on
+    // B200 at 1024^3 (CUDA-graph replay, so no launch overhead): whole slab 38.1 ms, groups of 8 / 4 / 2 / 1 planes
+    // 37.5 / 38.8 / 42.8 / 62.0 ms - the small launches lose more than the L2 gives back, so the default is the
+    // whole slab in one go.
+    const int64_t nxh = n / 2 + 1;
+    int64_t group = nz_local;
+    if (const char* e = getenv("FAVA_XY_GROUP")) {
+        const long v = atol(e);
+        if (v > 0) group = v;
+    }
+    group = std::min<int64_t>(group, nz_local);
+    const size_t esz = dtype == FAVA_F64 ? 8 : 4;
+    double* w[3] = {d_wx, d_wy, d_wz};
+    for (int64_t z0 = 0; z0 < nz_local; z0 += group) {
+        const int64_t g = std::min<int64_t>(group, nz_local - z0);
+        const size_t in_off = (size_t)z0 * n * n * esz;
+        const size_t out_off = (size_t)z0 * n * 2 * nxh;  // doubles
+        rc = fava_ke_weight3(ctx, (const char*)d_rho + in_off, (const char*)d_ux + in_off, (const char*)d_uy + in_off,
+                             (const char*)d_uz + in_off, dtype, g * n, n, 2 * nxh, d_wx + out_off, d_wy + out_off,
+                             d_wz + out_off, stream);
+        if (rc) return rc;
+        for (int c = 0; c < 3; ++c) {
+            rc = fava_fft_xy(ctx, w[c] + out_off, g, n, n, stream);
+            if (rc) return rc;
+        }
+    }
+    return FAVA_OK;
+}
+
 int fava_spectrum_bin(fava_ctx* ctx, const double* d_fx, const double* d_fy, const double* d_fz, int64_t n,
                       int64_t ny_local, const int32_t* d_ky_of_local, const int32_t* d_local_of_ky, double norm,
                       double* d_sums, void* stream) {
@@ -441,12 +480,10 @@ int fava_ke_spectrum(fava_ctx* ctx, const void* d_rho, const void* d_ux, const v
             if (rc) return rc;
         }
     } else {
-        rc = fava_ke_weight3(ctx, d_rho, d_ux, d_uy, d_uz, dtype, n * n, n, 2 * nxh, (double*)w[0], (double*)w[1],
-                             (double*)w[2], stream);
+        rc = fava_ke_weight_fft_xy(ctx, d_rho, d_ux, d_uy, d_uz, dtype, n, n, (double*)w[0], (double*)w[1], (double*)w[2],
+                                   stream);
         if (rc) return rc;
         for (int c = 0; c < 3; ++c) {
-            rc = fava_fft_xy(ctx, (double*)w[c], n, n, n, stream);
-            if (rc) return rc;
             rc = fava_fft_z(ctx, (double*)w[c], n, n * nxh, stream);
             if (rc) return rc;
         }

@@ -365,6 +365,15 @@ def ke_weight3(rho, ux, uy, uz, wx: int, wy: int, wz: int) -> None:
                "fava_ke_weight3")
 
 
+def ke_weight_fft_xy(rho, ux, uy, uz, wx: int, wy: int, wz: int) -> None:
+    """Weighting + 2-D transform of a slab in L2-resident plane groups (fava_ke_weight_fft_xy)."""
+    nz, ny, nx = _check_fields(rho, ux, uy, uz)
+    ctx = get_context(rho.device)
+    _lib.check(ctx.lib.fava_ke_weight_fft_xy(ctx.handle, _ptr(rho), _ptr(ux), _ptr(uy), _ptr(uz), _dtype_code(rho), nz, nx,
+                                             C.c_void_p(wx), C.c_void_p(wy), C.c_void_p(wz), _stream(rho)),
+               "fava_ke_weight_fft_xy")
+
+
 def fft_xy(data: int, nz_local: int, ny: int, nx: int, dev) -> None:
     ctx = get_context(dev)
     _lib.check(ctx.lib.fava_fft_xy(ctx.handle, C.c_void_p(data), nz_local, ny, nx, _cur_stream(dev)), "fava_fft_xy")

@@ -183,6 +183,11 @@ int fava_fft_cols(fava_ctx* ctx, double* d_data, int64_t n, int64_t ncols, int64
 /* In-place batched 2-D FFT (cuFFT D2Z) of a slab: real [nz_local][ny][2*(nx/2+1)] (padded rows) ->
  * complex [nz_local][ny][nx/2+1] (interleaved re,im), transformed along x (halved) and y. */
 int fava_fft_xy(fava_ctx* ctx, double* d_data, int64_t nz_local, int64_t ny, int64_t nx, void* stream);
+/* K4 + the 2-D transform of a whole slab in one call (optionally in groups of FAVA_XY_GROUP z-planes; measured
+ * slower on B200, see csrc/spectrum.cu).  Outputs as fava_fft_xy: complex [nz_local][n][n/2+1] per component. */
+int fava_ke_weight_fft_xy(fava_ctx* ctx, const void* d_rho, const void* d_ux, const void* d_uy, const void* d_uz,
+                          int dtype, int64_t nz_local, int64_t n, double* d_wx, double* d_wy, double* d_wz,
+                          void* stream);
 /* In-place c2c FFTs (cuFFT Z2Z) along the slowest axis of complex [nz][rows] (rows = ny_local*(nx/2+1)). */
 int fava_fft_z(fava_ctx* ctx, double* d_data, int64_t nz, int64_t rows, void* stream);
 /* Slab -> ky-pencil exchange, fused with the pack: rank `my_rank` holds complex [nz_local][n][nxh] after

@@ -301,3 +301,53 @@ def test_native_fft_path_matches_cufft_path(cuda_device, monkeypatch, n, dtype):
     library = device.ke_spectrum(rho, *u)
     for k in ("k", "total", "longitudinal", "transverse"):
         maxnorm_close(native[k], library[k], 1e-13, f"{k} n={n}")
+
+
+def test_staging_file_and_host_paths_are_byte_exact(cuda_device, tmp_path):
+    """fava_stage_h2d (pread -> pinned ring -> async H2D) and fava_stage_host_h2d deliver the dataset's bytes
+    unchanged, for sizes around the 16 MiB chunk / 2 MiB slice boundaries and odd tails."""
+    import torch
+
+    from fava_b200 import device
+
+    rng = np.random.default_rng(3)
+    for nfloat in (1, 1000, (2 << 20) // 4 + 3, (16 << 20) // 4, (40 << 20) // 4 + 17):
+        a = rng.random(nfloat, dtype=np.float32)
+        path = tmp_path / f"s{nfloat}_hdf5_plt_cnt_0000"
+        with h5lite.File(path, "w") as f:
+            f.create_dataset("dens", data=a)
+        with h5lite.File(path) as f:
+            off, nbytes = f["dens"].extent()
+        out = torch.empty(nfloat, dtype=torch.float32, device=cuda_device)
+        device.stage_file(path, off, nbytes, out)
+        assert np.array_equal(out.cpu().numpy(), a)
+        out2 = torch.zeros(nfloat, dtype=torch.float32, device=cuda_device)
+        device.stage_host(a, out2)
+        assert torch.equal(out, out2)
+    with pytest.raises(RuntimeError):
+        device.stage_file(tmp_path / "missing", 0, 16, torch.empty(4, dtype=torch.float32, device=cuda_device))
+    with pytest.raises(RuntimeError):  # dataset shorter than requested
+        device.stage_file(path, off, nbytes + (1 << 20), torch.empty(nfloat + (1 << 18), dtype=torch.float32, device=cuda_device))
+
+
+def test_reynolds_time_series_over_plt_files(fava, tmp_path):
+    """BASELINE configs[4] in miniature: the pipeline's per-file loop (reference __main__.py:76-97) over multi-block
+    plt files; every file's profile equals the oracle's on the assembled uniform array."""
+    from fava_b200 import series
+
+    mesh = synth.multiblock_mesh((2, 2, 2), (16, 16, 16))
+    fulls = []
+    for i in range(3):
+        full = synth.uniform_fields((32, 32, 32), names=FIELDS, dtype=np.float32, seed=100 + i)
+        fulls.append(full)
+        synth.write_flash_file(tmp_path / f"ts_hdf5_plt_cnt_{i:04d}", mesh,
+                               {k: synth.blocks_from_uniform(mesh, v) for k, v in full.items()}, time=0.5 * i)
+    model = fava.flash(tmp_path)
+    res, timing = series.reynolds_series(model, axis=0)
+    assert timing["files"] == 3 and timing["staged_bytes_this_rank"] == 3 * 4 * 32**3 * 4
+    for i, (t, radius, stress, means) in enumerate(res):
+        assert t == 0.5 * i
+        geom = orc.uniform_geom((32, 32, 32), bbox_dtype=np.float32)
+        _, s0, m0 = orc.reynolds_stress(geom, oracle_data(fulls[i]), axis=0)
+        for k in STRESS:
+            maxnorm_close(stress[k], s0[k], RTOL, f"file {i} {k}")
