@@ -221,6 +221,55 @@ __global__ void k_reduce_partials(const double* __restrict__ partial, int nchunk
     mom[idx] = accumulate ? mom[idx] + s : s;
 }
 
+// Fused x+z pass: with one chunk per z-plane, the column partials of plane z (13 moments per x, about the
+// x-pivots) also determine the z-bin moments: re-express each about the plane's own pivot (exact algebra, as
+// k_repivot) and add over x in a fixed order.  One CTA per plane.
+__global__ void __launch_bounds__(256)
+    k_partials_to_planes(const double* __restrict__ partial, int64_t nx, int64_t nz, double cells_per_column,
+                         const double* __restrict__ piv_x, const double* __restrict__ piv_z,
+                         double* __restrict__ mom_z, double cells_per_plane) {
+    const int64_t z = blockIdx.x;
+    const double* P = partial + z * kNM * nx;
+    const double cz[3] = {piv_z[z], piv_z[nz + z], piv_z[2 * nz + z]};
+    double acc[kNM];
+#pragma unroll
+    for (int m = 0; m < kNM; ++m) acc[m] = 0.0;
+    for (int64_t x = threadIdx.x; x < nx; x += blockDim.x) {
+        double q[kNM];
+#pragma unroll
+        for (int m = 0; m < kNM; ++m) q[m] = P[(int64_t)m * nx + x];
+        double e[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) e[i] = piv_x[i * nx + x] - cz[i];
+        acc[0] += q[0];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            acc[1 + i] += q[1 + i] + cells_per_column * e[i];
+            acc[4 + i] += q[4 + i] + e[i] * q[0];
+        }
+        int k = 7;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = i; j < 3; ++j, ++k) acc[k] += q[k] + e[i] * q[4 + j] + e[j] * q[4 + i] + e[i] * e[j] * q[0];
+    }
+    __shared__ double sm[kNM][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int m = 0; m < kNM; ++m) {
+        const double v = warp_sum_fixed(acc[m]);
+        if (lane == 0) sm[m][warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < kNM) {
+        double v = sm[threadIdx.x][0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) v += sm[threadIdx.x][w];
+        mom_z[(int64_t)threadIdx.x * nz + z] = v;
+    }
+    if (threadIdx.x == kNM) mom_z[(int64_t)kNM * nz + z] = cells_per_plane;
+}
+
 template <typename T>
 __global__ void k_plane_pivots(const T* __restrict__ ux, const T* __restrict__ uy, const T* __restrict__ uz,
                                int64_t stride, int64_t nbins, double* __restrict__ piv) {
@@ -362,6 +411,42 @@ static int launch_dense(fava_ctx* ctx, const T* rho, const T* ux, const T* uy, c
     return FAVA_OK;
 }
 
+template <typename T, int V, int U>
+static int launch_xz(fava_ctx* ctx, const T* rho, const T* ux, const T* uy, const T* uz, int64_t nz, int64_t ny,
+                     int64_t nx, const double* piv_x, const double* piv_z, double* mom_x, double* mom_z,
+                     cudaStream_t st) {
+    const int64_t strips = ceil_div(nx, 32 * V);
+    void* ws;
+    int rc = ctx_workspace(ctx, WS_PARTIALS, sizeof(double) * (size_t)nz * kNM * nx, &ws);
+    if (rc) return rc;
+    double* partial = (double*)ws;
+    dim3 grid((unsigned)strips, (unsigned)nz);  // one chunk of ny rows per z-plane
+    k_moments_cols<T, V, U, kNM><<<grid, kThreads, 0, st>>>(rho, ux, uy, uz, nz * ny, nx, piv_x, partial, ny);
+    FAVA_LAUNCHED();
+    const int64_t n = (int64_t)FAVA_NMOM * nx;
+    k_reduce_partials<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(partial, (int)nz, nx, kNM, FAVA_NMOM, mom_x, 0,
+                                                                 (double)(nz * ny));
+    FAVA_LAUNCHED();
+    k_partials_to_planes<<<(unsigned)nz, 256, 0, st>>>(partial, nx, nz, (double)ny, piv_x, piv_z, mom_z,
+                                                      (double)(nx * ny));
+    FAVA_LAUNCHED();
+    return FAVA_OK;
+}
+
+template <typename T, int U>
+static int dispatch_xz(fava_ctx* ctx, const void* rho, const void* ux, const void* uy, const void* uz, int64_t nz,
+                       int64_t ny, int64_t nx, const double* piv_x, const double* piv_z, double* mom_x,
+                       double* mom_z, cudaStream_t st) {
+    const size_t va = 2 * sizeof(T);
+    const bool vec = (nx % 2 == 0) && aligned_to(rho, va) && aligned_to(ux, va) && aligned_to(uy, va) &&
+                     aligned_to(uz, va);
+    if (vec)
+        return launch_xz<T, 2, U>(ctx, (const T*)rho, (const T*)ux, (const T*)uy, (const T*)uz, nz, ny, nx, piv_x,
+                                  piv_z, mom_x, mom_z, st);
+    return launch_xz<T, 1, U>(ctx, (const T*)rho, (const T*)ux, (const T*)uy, (const T*)uz, nz, ny, nx, piv_x, piv_z,
+                              mom_x, mom_z, st);
+}
+
 template <typename T, int U, int NM>
 static int dispatch_dense(fava_ctx* ctx, const void* rho, const void* ux, const void* uy, const void* uz,
                           int64_t nz, int64_t ny, int64_t nx, int axis, const double* piv, double* mom,
@@ -420,6 +505,21 @@ int fava_plane_moments(fava_ctx* ctx, const void* d_rho, const void* d_ux, const
                                          accumulate, st);
     return dispatch_dense<float, 8, kNM>(ctx, d_rho, d_ux, d_uy, d_uz, nz, ny, nx, axis, d_pivots, d_moments,
                                     accumulate, st);
+}
+
+int fava_plane_moments_xz(fava_ctx* ctx, const void* d_rho, const void* d_ux, const void* d_uy, const void* d_uz,
+                          int dtype, int64_t nz, int64_t ny, int64_t nx, const double* d_piv_x,
+                          const double* d_piv_z, double* d_mom_x, double* d_mom_z, void* stream) {
+    FAVA_REQUIRE(ctx && d_rho && d_ux && d_uy && d_uz && d_piv_x && d_piv_z && d_mom_x && d_mom_z,
+                 "fava_plane_moments_xz: NULL argument");
+    FAVA_REQUIRE(nz > 0 && ny > 0 && nx > 0 && nz <= 65535, "fava_plane_moments_xz: bad shape %lldx%lldx%lld",
+                 (long long)nz, (long long)ny, (long long)nx);
+    FAVA_REQUIRE(dtype == FAVA_F32 || dtype == FAVA_F64, "fava_plane_moments_xz: bad dtype %d", dtype);
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == FAVA_F64)
+        return dispatch_xz<double, 4>(ctx, d_rho, d_ux, d_uy, d_uz, nz, ny, nx, d_piv_x, d_piv_z, d_mom_x, d_mom_z, st);
+    return dispatch_xz<float, 8>(ctx, d_rho, d_ux, d_uy, d_uz, nz, ny, nx, d_piv_x, d_piv_z, d_mom_x, d_mom_z, st);
 }
 
 int fava_plane_sum(fava_ctx* ctx, const void* d_field, int dtype, int64_t nz, int64_t ny, int64_t nx, int axis,

@@ -69,8 +69,8 @@ constexpr int kBinWarps = kBinT / 32;
 constexpr int kSlots = 64;     // shell span of one tile (<= 31*sqrt(2) + 2)
 
 struct BinParams {
-    int n, nxh, ny_local, nbins, kmax2, ntx, ntz;
-    int64_t ntiles;
+    int n, nxh, ny_local, nbins, kmax2, npairs;
+    int64_t ngroups;
     int64_t zstride;  // ny_local * nxh (complex elements per kz plane)
     const int32_t* ky_of_local;  // NULL = identity (local row jl holds global ky index jl)
     const int32_t* local_of_ky;  // NULL = identity
@@ -93,6 +93,18 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool va
 }
 
 // dynamic shared memory: [3][nbins] CTA bins | [3][32][33] transposed operand tiles | [3][8][64] warp bins
+//
+// Work unit = a GROUP of up to eight 32x32 tiles that touch the same memory: for a ky row j >= 0 (and its mirror
+// -ky, row jm) and an unordered pair {a, b} of 32-wide index ranges, the tiles (kx in A, |kz| in B) and
+// (kx in B, |kz| in A), for kz >= 0 and kz < 0, in planes j and jm.  The direct operand of one member is the
+// transposed operand of the next, so a CTA that walks a group back to back reads every element from DRAM once
+// and finds it in L2 the second time (ncu: 32.4 GB -> see profiles/).
+struct BinTile {
+    int jl, jml, ky;  // local ky row of the points, local row of -ky, wavenumber
+    int a, b;         // kx tile, |kz| tile
+    int neg;          // 1: kz = -(32 b + i), else kz = 32 b + i
+};
+
 __global__ void __launch_bounds__(kBinT, 2)
     k_spectrum_bin(const double2* __restrict__ fx, const double2* __restrict__ fy, const double2* __restrict__ fz,
                    BinParams p, double* __restrict__ partial) {
@@ -117,51 +129,40 @@ __global__ void __launch_bounds__(kBinT, 2)
     const int n = p.n, nh = n >> 1;
     const double2* F[3] = {fx, fy, fz};
 
-    for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-        const int tx = (int)(tile % p.ntx);
-        const int tz = (int)((tile / p.ntx) % p.ntz);
-        const int jl = (int)(tile / ((int64_t)p.ntx * p.ntz));
-        const int j = p.ky_of_local ? p.ky_of_local[jl] : jl;
-        if (j < 0 || j == nh) continue;  // padding row / Nyquist ky plane (beyond the last bin)
-        const int ky = j < nh ? j : j - n;
-        const int a0 = tx * kTS, b0 = tz * kTS;
-        const int lend = min(b0 + kTS - 1, n - 1);
-        const int f0 = b0 < nh ? b0 : n - b0, f1 = lend < nh ? lend : n - lend;
-        const int kzmin = min(f0, f1);
-        const int k2min = a0 * a0 + ky * ky + kzmin * kzmin;
-        if (k2min > p.kmax2) continue;  // tile outside the sphere (uniform for the CTA)
-        const int mlo = shell_of(k2min);
-        const int jm = (n - j) % n;
-        const int jml = p.local_of_ky ? p.local_of_ky[jm] : jm;
-
+    auto process = [&](const BinTile& T) {
+        const int a0 = T.a * kTS, b0 = T.b * kTS;
+        const int kzlo = T.neg ? max(b0, 1) : b0;
+        const int mlo = shell_of(a0 * a0 + T.ky * T.ky + kzlo * kzlo);
         // ---- phase A: all three transposed operand tiles in flight (no registers held) -------------------
-        // S[c][a][b] = stored value whose (conjugate, if kz(b) < 0) is u^_c at (x-wn = kz(b), y-wn = ky, z-wn = kx(a))
+        // S[c][ia][ib] = stored value whose (conjugate, if kz < 0) is u^_c at (x-wn = kz, y-wn = ky, z-wn = kx),
+        // kx = a0 + ia, |kz| = b0 + ib; lanes run over ib (contiguous x index in memory)
         {
-            const int l = b0 + lane;  // kz index handled by this lane while loading
-            const bool lok = l < n && l != nh;
+            const int q = b0 + lane;  // |kz| handled by this lane while loading
+            const bool qok = q < nh && !(T.neg && q == 0);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int a = warp + kBinWarps * i;  // kx_local of the row being loaded
-                const int kxa = a0 + a;
-                const bool ok = lok && kxa < nh;
+                const int ia = warp + kBinWarps * i;
+                const int kxa = a0 + ia;
+                const bool ok = qok && kxa < nh;
                 int64_t off = 0;
-                if (ok) off = l < nh ? (int64_t)kxa * p.zstride + (int64_t)jl * p.nxh + l
-                                     : (int64_t)((n - kxa) % n) * p.zstride + (int64_t)jml * p.nxh + (n - l);
+                if (ok) off = T.neg ? (int64_t)((n - kxa) % n) * p.zstride + (int64_t)T.jml * p.nxh + q
+                                    : (int64_t)kxa * p.zstride + (int64_t)T.jl * p.nxh + q;
 #pragma unroll
-                for (int c = 0; c < 3; ++c) cp_async16(&S[c][a][lane], F[c] + off, ok);
+                for (int c = 0; c < 3; ++c) cp_async16(&S[c][ia][lane], F[c] + off, ok);
             }
             asm volatile("cp.async.commit_group;\n" ::);
         }
-        // ---- phase B: this thread's own points: kx = a0 + lane, kz rows b0 + warp + 8 i ------------------
+        // ---- phase B: this thread's own points: kx = a0 + lane, |kz| = b0 + warp + 8 i -------------------
         const int kx = a0 + lane;
         double tot[4];
         {
             double2 d[3][4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int l = b0 + warp + kBinWarps * i;
-                const bool ok = kx < nh && l < n && l != nh;
-                const int64_t off = ok ? (int64_t)l * p.zstride + (int64_t)jl * p.nxh + kx : 0;
+                const int q = b0 + warp + kBinWarps * i;
+                const bool ok = kx < nh && q < nh && !(T.neg && q == 0);
+                const int l = T.neg ? n - q : q;
+                const int64_t off = ok ? (int64_t)l * p.zstride + (int64_t)T.jl * p.nxh + kx : 0;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) d[c][i] = ok ? __ldcs(F[c] + off) : make_double2(0.0, 0.0);
             }
@@ -178,18 +179,18 @@ __global__ void __launch_bounds__(kBinT, 2)
         // ---- phase C: projection, shell index, warp-level segmented reduction ---------------------------
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int b = warp + kBinWarps * i;  // kz_local
-            const int l = b0 + b;
+            const int ib = warp + kBinWarps * i;
+            const int q = b0 + ib;
             int key = -1;
             double vt = 0.0, vl = 0.0, vc = 0.0;
-            if (kx < nh && l < n && l != nh) {
-                const int kz = l < nh ? l : l - n;
-                const int k2 = kx * kx + ky * ky + kz * kz;
+            if (kx < nh && q < nh && !(T.neg && q == 0)) {
+                const int kz = T.neg ? -q : q;
+                const int k2 = kx * kx + T.ky * T.ky + kz * kz;
                 if (k2 <= p.kmax2) {
-                    const double sgn = l < nh ? 1.0 : -1.0;  // conjugate of the folded half
-                    const double2 t0 = S[0][lane][b], t1 = S[1][lane][b], t2 = S[2][lane][b];
-                    const double lre = fma((double)kx, t0.x, fma((double)ky, t1.x, (double)kz * t2.x));
-                    const double lim = sgn * fma((double)kx, t0.y, fma((double)ky, t1.y, (double)kz * t2.y));
+                    const double sgn = T.neg ? -1.0 : 1.0;  // conjugate of the folded half
+                    const double2 t0 = S[0][lane][ib], t1 = S[1][lane][ib], t2 = S[2][lane][ib];
+                    const double lre = fma((double)kx, t0.x, fma((double)T.ky, t1.x, (double)kz * t2.x));
+                    const double lim = sgn * fma((double)kx, t0.y, fma((double)T.ky, t1.y, (double)kz * t2.y));
                     key = shell_of(k2);
                     const double w = kx == 0 ? 1.0 : 2.0;
                     vt = w * 0.5 * tot[i] * p.norm2;
@@ -227,6 +228,52 @@ __global__ void __launch_bounds__(kBinT, 2)
             if (m < p.nbins && sc != 0.0) cta_tot[m] += st, cta_lon[m] += sl, cta_cnt[m] += sc;
         }
         // the next tile's first __syncthreads (after its loads) orders these bin updates
+    };
+
+    for (int64_t g = blockIdx.x; g < p.ngroups; g += gridDim.x) {
+        const int pr = (int)(g % p.npairs);
+        const int jl = (int)(g / p.npairs);  // positive-ky rows are the first npos local rows
+        // unordered pair {a, b}, a <= b, from the linear index pr = b (b + 1) / 2 + a
+        int b = (int)((sqrt(8.0 * pr + 1.0) - 1.0) * 0.5);
+        while ((b + 1) * (b + 2) / 2 <= pr) ++b;
+        while (b * (b + 1) / 2 > pr) --b;
+        const int a = pr - b * (b + 1) / 2;
+        const int j = p.ky_of_local ? p.ky_of_local[jl] : jl;
+        if (j < 0 || j >= nh) continue;
+        const int ky = j;
+        if (a * a * kTS * kTS + b * b * kTS * kTS + ky * ky > p.kmax2) continue;  // whole group outside the sphere
+        const int jm = (n - j) % n;
+        const int jml = p.local_of_ky ? p.local_of_ky[jm] : jm;
+        const bool self = jm == j;  // ky = 0
+        BinTile T;
+        T.jl = jl, T.jml = jml, T.ky = ky, T.a = a, T.b = b, T.neg = 0;
+        process(T);  // M1: plane +ky, (A, +B)
+        if (a != b) {
+            T.a = b, T.b = a;
+            process(T);  // M2: plane +ky, (B, +A)
+        }
+        T.a = a, T.b = b, T.neg = 1;
+        process(T);  // M3: plane +ky, (A, -B)
+        if (!self) {
+            T.jl = jml, T.jml = jl, T.ky = -ky, T.a = b, T.b = a;
+            process(T);  // M4: plane -ky, (B, -A): its operands are M3's, swapped
+        }
+        if (a != b) {
+            T.jl = jl, T.jml = jml, T.ky = ky, T.a = b, T.b = a;
+            process(T);  // M5: plane +ky, (B, -A)
+            if (!self) {
+                T.jl = jml, T.jml = jl, T.ky = -ky, T.a = a, T.b = b;
+                process(T);  // M6: plane -ky, (A, -B)
+            }
+        }  // a == b: M4 already covered plane -ky, (A, -A)
+        if (!self) {
+            T.jl = jml, T.jml = jl, T.ky = -ky, T.neg = 0, T.a = a, T.b = b;
+            process(T);  // M7: plane -ky, (A, +B)
+            if (a != b) {
+                T.a = b, T.b = a;
+                process(T);  // M8: plane -ky, (B, +A)
+            }
+        }
     }
     __syncthreads();
     double* out = partial + (int64_t)blockIdx.x * 3 * p.nbins;
@@ -402,15 +449,18 @@ int fava_spectrum_bin(fava_ctx* ctx, const double* d_fx, const double* d_fy, con
     p.n = (int)n, p.nxh = (int)(n / 2 + 1), p.ny_local = (int)ny_local;
     p.nbins = (int)(n / 2 - 1);
     p.kmax2 = (int)(n * n / 4 - 3 * n / 2 + 2);
-    p.ntx = (int)((n / 2 + kTS - 1) / kTS);
-    p.ntz = (int)((n + kTS - 1) / kTS);
-    p.ntiles = (int64_t)p.ntx * p.ntz * ny_local;
+    const int nt = (int)((n / 2 + kTS - 1) / kTS);  // 32-wide tiles of kx and of |kz|
+    p.npairs = nt * (nt + 1) / 2;
+    // rows with ky >= 0 come first: all n/2 of them on one GPU (identity map), the first half of a rank's
+    // +-ky symmetric set otherwise (fava_b200/spectrum.py:ky_ownership)
+    const int64_t npos = d_ky_of_local ? (ny_local + 1) / 2 : n / 2;
+    p.ngroups = npos * p.npairs;
     p.zstride = ny_local * (int64_t)p.nxh;
     p.ky_of_local = d_ky_of_local, p.local_of_ky = d_local_of_ky;
     p.norm2 = norm * norm;
     const size_t nb_pad = (size_t)((3 * p.nbins + 1) & ~1);
     const size_t dyn = sizeof(double) * (nb_pad + 3 * kBinWarps * kSlots) + 3 * sizeof(double2) * kTS * (kTS + 1);
-    const int ncta = (int)std::min<int64_t>(p.ntiles, (int64_t)ctx->num_sms * 2);
+    const int ncta = (int)std::min<int64_t>(p.ngroups, (int64_t)ctx->num_sms * 2);
     void* ws;
     rc = ctx_workspace(ctx, WS_PARTIALS, sizeof(double) * 3 * (size_t)p.nbins * ncta, &ws);
     if (rc) return rc;

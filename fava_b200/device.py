@@ -130,6 +130,22 @@ def plane_moments(rho, ux, uy, uz, axis: int, pivots: torch.Tensor | None = None
     return out, pivots
 
 
+def plane_moments_xz(rho, ux, uy, uz):
+    """Moments for axis x and axis z from one pass (fava_plane_moments_xz) -> ((mom_x, piv_x), (mom_z, piv_z))."""
+    nz, ny, nx = _check_fields(rho, ux, uy, uz)
+    ctx = get_context(rho.device)
+    piv_x = plane_pivots(ux, uy, uz, 0)
+    piv_z = plane_pivots(ux, uy, uz, 2)
+    mom_x = torch.empty((FAVA_NMOM, nx), dtype=torch.float64, device=rho.device)
+    mom_z = torch.empty((FAVA_NMOM, nz), dtype=torch.float64, device=rho.device)
+    _lib.check(
+        ctx.lib.fava_plane_moments_xz(ctx.handle, _ptr(rho), _ptr(ux), _ptr(uy), _ptr(uz), _dtype_code(rho), nz, ny, nx,
+                                      _ptr(piv_x), _ptr(piv_z), _ptr(mom_x), _ptr(mom_z), _stream(rho)),
+        "fava_plane_moments_xz",
+    )
+    return (mom_x, piv_x), (mom_z, piv_z)
+
+
 def moments_repivot(moments: torch.Tensor, piv_old: torch.Tensor, piv_new: torch.Tensor) -> None:
     ctx = get_context(moments.device)
     nbins = int(moments.shape[1])

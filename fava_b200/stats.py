@@ -97,7 +97,11 @@ def slab_step(rho, ux, uy, uz, n: int, cell_volume: float, layer_volume: float, 
     out, pending = {}, {}
 
     def local_moments():
-        for ax in axes:
+        todo = list(axes)
+        if 0 in todo and 2 in todo:  # x and z bins from ONE pass over the slab
+            pending[0], pending[2] = device.plane_moments_xz(rho, ux, uy, uz)
+            todo = [ax for ax in todo if ax == 1]
+        for ax in todo:
             pending[ax] = slab_moments_local(rho, ux, uy, uz, ax)
 
     def finish_profiles():

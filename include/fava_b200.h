@@ -87,6 +87,14 @@ int fava_plane_moments(fava_ctx* ctx, const void* d_rho, const void* d_ux, const
                        const void* d_uz, int dtype, int64_t nz, int64_t ny, int64_t nx, int axis,
                        const double* d_pivots, double* d_moments, int accumulate, void* stream);
 
+/* Axis x AND axis z from ONE pass over the data: the column kernel runs with one chunk per z-plane; its per-plane
+ * column partials are summed over z for the x-bins and, re-expressed about the plane pivots (exact algebra),
+ * over x for the z-bins.  Saves one of the three passes of an x/y/z profile set.
+ * d_piv_x [3][nx], d_piv_z [3][nz] (fava_plane_pivots with axis 0 / 2); d_mom_x [FAVA_NMOM][nx], d_mom_z [FAVA_NMOM][nz]. */
+int fava_plane_moments_xz(fava_ctx* ctx, const void* d_rho, const void* d_ux, const void* d_uy, const void* d_uz,
+                          int dtype, int64_t nz, int64_t ny, int64_t nx, const double* d_piv_x,
+                          const double* d_piv_z, double* d_mom_x, double* d_mom_z, void* stream);
+
 /* Block-list front end for FLASH block datasets [nblocks][nzb][nyb][nxb] (AMR or multi-block
  * uniform plt files).  For leaf l of the table: planes i=0..nrb-1 of block blk[l] normal to `axis`
  * contribute weight vf[l] to fine bins [ilo[l]+i*scale[l], ilo[l]+(i+1)*scale[l])

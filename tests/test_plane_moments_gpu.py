@@ -172,3 +172,29 @@ def test_bad_arguments_raise(cuda_device):
     with pytest.raises(ValueError):
         c = x.cpu()
         device.plane_moments(c, c, c, c, 0)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("shape", [(64, 64, 64), (24, 40, 56), (7, 9, 11)])
+def test_fused_xz_pass_matches_single_axis_passes(cuda_device, dtype, shape):
+    """fava_plane_moments_xz: x-bins and z-bins from one pass (z from the per-plane column partials, re-pivoted)
+    == the dedicated axis-0 and axis-2 passes, after finalisation, to 1e-13; and vs the oracle to 1e-12."""
+    import torch
+
+    from fava_b200 import device
+
+    f = synth.uniform_fields(shape, names=("dens", "velx", "vely", "velz"), dtype=dtype, seed=21, u0=5.0)
+    t = [torch.from_numpy(f[k].copy()).to(cuda_device) for k in ("dens", "velx", "vely", "velz")]
+    (mx, px), (mz, pz) = device.plane_moments_xz(*t)
+    nz, ny, nx = shape
+    cv = 1.0 / (nx * ny * nz)
+    for axis, mom, piv, n in ((0, mx, px, nx), (2, mz, pz, nz)):
+        lv = 1.0 / n
+        fused = device.moments_finalize(mom, piv, cv, lv)
+        single = device.plane_profiles(*t, axis, cv, lv)
+        for k in fused:
+            maxnorm_close(fused[k].cpu().numpy(), single[k].cpu().numpy(), rtol=1e-13, what=f"xz {k} axis {axis}")
+    compare(f, 0, ((0.0, 1.0), (0.0, 1.0), (0.0, 1.0)), cuda_device)
+    a, _ = device.plane_moments_xz(*t)
+    b, _ = device.plane_moments_xz(*t)
+    assert torch.equal(a[0], b[0])
