@@ -37,13 +37,18 @@ def _counters(seed: int, field: str, stream: int, lin: np.ndarray) -> np.ndarray
 
 
 def field_slab(name: str, shape_zyx: tuple[int, int, int], z0: int = 0, nz: int | None = None, *, seed: int = 1234,
-               amp: float = 1.0, sigma: float = 0.25, u0: float = 0.0, dtype=np.float64) -> np.ndarray:
-    """Planes [z0, z0+nz) of field `name` for a global grid `shape_zyx`, in file order [z][y][x]."""
+               amp: float = 1.0, sigma: float = 0.25, u0: float = 0.0, dtype=np.float64, y0: int = 0,
+               ny: int | None = None, x0: int = 0, nx: int | None = None) -> np.ndarray:
+    """The sub-box [z0,z0+nz) x [y0,y0+ny) x [x0,x0+nx) (default: whole planes) of field `name` for a global grid
+    `shape_zyx`, in file order [z][y][x]; every cell depends only on its global index, so any piece can be
+    generated independently and bit-identically."""
     NZ, NY, NX = shape_zyx
     nz = NZ - z0 if nz is None else nz
+    ny = NY - y0 if ny is None else ny
+    nx = NX - x0 if nx is None else nx
     z = np.arange(z0, z0 + nz, dtype=np.int64)[:, None, None]
-    y = np.arange(NY, dtype=np.int64)[None, :, None]
-    x = np.arange(NX, dtype=np.int64)[None, None, :]
+    y = np.arange(y0, y0 + ny, dtype=np.int64)[None, :, None]
+    x = np.arange(x0, x0 + nx, dtype=np.int64)[None, None, :]
     lin = (z * NY + y) * NX + x
     if name == "dens":
         out = 1.0 + 0.5 * _uniform01(_counters(seed, name, 0, lin))
@@ -58,7 +63,7 @@ def field_slab(name: str, shape_zyx: tuple[int, int, int], z0: int = 0, nz: int 
         coord = ((y + 0.5) / NY, (z + 0.5) / NZ, (x + 0.5) / NX)[c]
         mode = (1, 2, 3)[c]
         out = amp * np.sin(2.0 * np.pi * mode * coord) + sigma * gauss + u0
-        out = np.broadcast_to(out, (nz, NY, NX))
+        out = np.broadcast_to(out, (nz, ny, nx))
     else:
         raise KeyError(name)
     return np.ascontiguousarray(out, dtype=dtype)
@@ -206,8 +211,8 @@ def block_fields(mesh: SynthMesh, names=("dens", "velx", "vely", "velz", "pres")
         NZ, NY, NX = mesh.nroot[2] * mesh.nzb * s, mesh.nroot[1] * mesh.nyb * s, mesh.nroot[0] * mesh.nxb * s
         ox, oy, oz = (int(v) for v in mesh.origin[b])
         for n in names:
-            slab = field_slab(n, (NZ, NY, NX), z0=oz * mesh.nzb, nz=mesh.nzb, seed=seed + 7919 * l, **kw)
-            out[n][b] = slab[:, oy * mesh.nyb : (oy + 1) * mesh.nyb, ox * mesh.nxb : (ox + 1) * mesh.nxb]
+            out[n][b] = field_slab(n, (NZ, NY, NX), z0=oz * mesh.nzb, nz=mesh.nzb, y0=oy * mesh.nyb, ny=mesh.nyb,
+                                   x0=ox * mesh.nxb, nx=mesh.nxb, seed=seed + 7919 * l, **kw)
     for b in sorted(kids, reverse=True):  # pre-order => children have larger ids; fill deepest first
         for n in names:
             acc = np.zeros((mesh.nzb, mesh.nyb, mesh.nxb))
