@@ -50,7 +50,8 @@ int set_error(int code, const char* fmt, ...);
 constexpr int kNumSMsB200 = 148;
 
 enum WorkspaceSlot { WS_PARTIALS = 0, WS_TABLE = 1, WS_AUX = 2, WS_FFT0 = 3, WS_FFT1 = 4, WS_FFT2 = 5,
-                     WS_FFTIN = 6, WS_BINMAP = 7, WS_USER0 = FAVA_WS_USER0, WS_COUNT = FAVA_WS_NSLOTS };
+                     WS_FFTIN = 6, WS_BINMAP = 7, WS_USER0 = FAVA_WS_USER0, WS_ITEMS0 = 16 /* +axis: cached block-list tables */,
+                     WS_COUNT = FAVA_WS_NSLOTS };
 
 struct Staging;  // pinned ring + reader threads (staging.cu)
 
@@ -64,6 +65,9 @@ struct fava_ctx {
     // cuFFT plans keyed by (kind, a, b, c)
     std::map<std::tuple<int, int64_t, int64_t, int64_t>, cufftHandle> plans;
     std::map<std::tuple<int, int64_t, int64_t, int64_t>, size_t> plan_work;  // work-area bytes per plan
+    // host copies of the leaf tables whose device CSR tables are cached in WS_ITEMS0 + axis (block_moments.cu)
+    std::string item_cache_key[3];
+    std::string prolong_cache_key;  // same for the lattice table of fava_prolong (WS_TABLE)
     std::map<int64_t, void*> twiddles;  // exp(-2 pi i m / N) tables of the native FFT, per N
     fava::Staging* staging = nullptr;
 };

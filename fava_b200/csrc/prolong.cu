@@ -7,9 +7,11 @@
 //   tile (X/nxb, Y/nyb, Z/nzb) of the fine grid  ->  index of the leaf that owns it
 // (leaves are written in list order, so a later leaf overwrites an earlier one exactly like the dict
 // does, and tiles nobody owns stay -1 => 0.0 as in_data[...] = 0.0, :1258).  The kernel is a pure
-// gather: one thread per pair of fine cells, source cell = (fine - corner) / scale, coalesced 16 B
-// stores of the fp64 result in FILE order [Z][Y][X].  Bit-exact (f32 -> f64 widening is exact).
+// gather, one CTA per tile: source cell = (fine - corner) >> log2(scale), stores in FILE order [Z][Y][X].
+// Bit-exact (f32 -> f64 widening is exact).
 // Traffic: every selected source cell is read once from HBM (repeats hit L1/L2), 8 B written per cell.
+#include <cstring>
+#include <string>
 #include <vector>
 
 #include "common.cuh"
@@ -23,41 +25,41 @@ struct ProlongGeom {
     int64_t NX, NY, NZ;    // output dims
 };
 
-template <typename T>
-__device__ __forceinline__ double prolong_cell(const T* __restrict__ blocks, const fava_prolong_leaf* __restrict__ leaves,
-                                               const int32_t* __restrict__ table, const ProlongGeom& g, int64_t X,
-                                               int64_t Y, int64_t Z) {
-    const int tx = (int)((X - g.sx + g.nxb) / g.nxb);
-    const int ty = (int)((Y - g.sy + g.nyb) / g.nyb);
-    const int tz = (int)((Z - g.sz + g.nzb) / g.nzb);
-    const int32_t l = table[((int64_t)tz * g.ty + ty) * g.tx + tx];
-    if (l < 0) return 0.0;
-    const fava_prolong_leaf leaf = leaves[l];
-    const int i = (int)((X - leaf.off[0]) / leaf.scale);
-    const int j = (int)((Y - leaf.off[1]) / leaf.scale);
-    const int k = (int)((Z - leaf.off[2]) / leaf.scale);
-    return (double)blocks[((leaf.block * g.nzb + k) * g.nyb + j) * (int64_t)g.nxb + i];
-}
-
+// One CTA per lattice tile (nxb x nyb x nzb fine cells, all owned by ONE leaf): the table entry and the leaf
+// descriptor are read once per CTA, so each fine cell costs a single dependent load (the source value; repeats
+// for scale > 1 hit L1) and the stores are whole rows of the tile (nxb x 8 B contiguous).  32-bit index arithmetic;
+// scale is a power of two -> shift.
 template <typename T>
 __global__ void __launch_bounds__(256)
     k_prolong(const T* __restrict__ blocks, const fava_prolong_leaf* __restrict__ leaves,
               const int32_t* __restrict__ table, ProlongGeom g, double* __restrict__ out) {
-    const int64_t row = blockIdx.y + (int64_t)blockIdx.z * gridDim.y;  // row = Z*NY + Y
-    if (row >= g.NZ * g.NY) return;
-    const int64_t Z = row / g.NY, Y = row - Z * g.NY;
-    double* orow = out + row * g.NX;
-    const bool vec = ((g.NX & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-    for (int64_t X = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; X < g.NX;
-         X += (int64_t)gridDim.x * blockDim.x * 2) {
-        const double a = prolong_cell(blocks, leaves, table, g, X, Y, Z);
-        if (X + 1 < g.NX) {
-            const double b = prolong_cell(blocks, leaves, table, g, X + 1, Y, Z);
-            if (vec) __stcs(reinterpret_cast<double2*>(orow + X), make_double2(a, b));
-            else orow[X] = a, orow[X + 1] = b;
-        } else {
-            orow[X] = a;
+    const int64_t tile = blockIdx.x + (int64_t)blockIdx.y * gridDim.x;
+    if (tile >= (int64_t)g.tx * g.ty * g.tz) return;
+    const int tx = (int)(tile % g.tx), ty = (int)((tile / g.tx) % g.ty), tz = (int)(tile / ((int64_t)g.tx * g.ty));
+    // fine-cell box of the tile, clipped to the output
+    const int x0 = tx * g.nxb + g.sx - g.nxb, y0 = ty * g.nyb + g.sy - g.nyb, z0 = tz * g.nzb + g.sz - g.nzb;
+    const int xa = max(x0, 0), xb = (int)min((int64_t)x0 + g.nxb, g.NX);
+    const int ya = max(y0, 0), yb = (int)min((int64_t)y0 + g.nyb, g.NY);
+    const int za = max(z0, 0), zb = (int)min((int64_t)z0 + g.nzb, g.NZ);
+    const int wx = xb - xa, wy = yb - ya, wz = zb - za;
+    if (wx <= 0 || wy <= 0 || wz <= 0) return;
+    const int32_t l = table[tile];
+    const int ncell = wx * wy * wz;
+    if (l < 0) {  // nobody owns the tile: zeros (in_data[...] = 0.0, _flash.py:1258)
+        for (int c = threadIdx.x; c < ncell; c += blockDim.x) {
+            const int ix = c % wx, iy = (c / wx) % wy, iz = c / (wx * wy);
+            out[((int64_t)(za + iz) * g.NY + (ya + iy)) * g.NX + (xa + ix)] = 0.0;
         }
+        return;
+    }
+    const fava_prolong_leaf leaf = leaves[l];
+    const int sh = 31 - __clz(leaf.scale);
+    const T* src = blocks + leaf.block * ((int64_t)g.nzb * g.nyb * g.nxb);
+    for (int c = threadIdx.x; c < ncell; c += blockDim.x) {
+        const int ix = c % wx, iy = (c / wx) % wy, iz = c / (wx * wy);
+        const int X = xa + ix, Y = ya + iy, Z = za + iz;
+        const int i = (X - leaf.off[0]) >> sh, j = (Y - leaf.off[1]) >> sh, k = (Z - leaf.off[2]) >> sh;
+        __stcs(out + ((int64_t)Z * g.NY + Y) * g.NX + X, (double)src[(k * g.nyb + j) * g.nxb + i]);
     }
 }
 
@@ -81,48 +83,63 @@ static int run_prolong(fava_ctx* ctx, const T* blocks, int64_t nzb, int64_t nyb,
     g.ty = (int)cdivp(NY - g.sy, nyb) + 1;
     g.tz = (int)cdivp(NZ - g.sz, nzb) + 1;
     const int64_t ntile = (int64_t)g.tx * g.ty * g.tz;
-    std::vector<int32_t> table((size_t)ntile, -1);
-    for (int64_t l = 0; l < nleaf; ++l) {
-        const fava_prolong_leaf& d = h_leaves[l];
-        if (d.scale < 1 || d.block < 0)
-            return set_error(FAVA_EINVAL, "fava_prolong: leaf %lld has scale %d / block %lld", (long long)l, d.scale,
-                             (long long)d.block);
-        if (pmod(d.off[0], nxb) != g.sx || pmod(d.off[1], nyb) != g.sy || pmod(d.off[2], nzb) != g.sz)
-            return set_error(FAVA_EINVAL, "fava_prolong: leaf %lld corner (%d,%d,%d) is not on the block lattice",
-                             (long long)l, d.off[0], d.off[1], d.off[2]);
-        // tiles covered by the leaf, clipped to the table
-        int64_t lo[3], hi[3];
-        const int dims[3] = {g.tx, g.ty, g.tz};
-        bool empty = false;
-        for (int a = 0; a < 3; ++a) {
-            // off may be far negative: floor division
-            const int64_t nb = a == 0 ? nxb : (a == 1 ? nyb : nzb);
-            const int64_t num = (int64_t)d.off[a] - (a == 0 ? g.sx : (a == 1 ? g.sy : g.sz)) + nb;
-            const int64_t first = num >= 0 ? num / nb : -((-num + nb - 1) / nb);
-            lo[a] = std::max<int64_t>(first, 0);
-            hi[a] = std::min<int64_t>(first + d.scale, dims[a]);
-            if (hi[a] <= lo[a]) empty = true;
-        }
-        if (empty) continue;
-        for (int64_t z = lo[2]; z < hi[2]; ++z)
-            for (int64_t y = lo[1]; y < hi[1]; ++y)
-                for (int64_t x = lo[0]; x < hi[0]; ++x) table[(size_t)((z * g.ty + y) * g.tx + x)] = (int32_t)l;
-    }
     const size_t b_leaves = sizeof(fava_prolong_leaf) * (size_t)std::max<int64_t>(nleaf, 1);
     const size_t b_table = sizeof(int32_t) * (size_t)ntile;
-    void* tab;
-    int rc = ctx_workspace(ctx, WS_TABLE, b_leaves + b_table, &tab);
-    if (rc) return rc;
-    auto* d_leaves = (fava_prolong_leaf*)tab;
-    auto* d_table = (int32_t*)((char*)tab + b_leaves);
-    if (nleaf) FAVA_CHECK_CUDA(cudaMemcpyAsync(d_leaves, h_leaves, sizeof(fava_prolong_leaf) * nleaf, cudaMemcpyHostToDevice, st));
-    FAVA_CHECK_CUDA(cudaMemcpyAsync(d_table, table.data(), b_table, cudaMemcpyHostToDevice, st));
+    // from_amr prolongs several fields with ONE leaf list: an identical request re-uses the device tables
+    const int64_t head[7] = {nzb, nyb, nxb, NZ, NY, NX, nleaf};
+    const size_t key_bytes = sizeof(head) + sizeof(fava_prolong_leaf) * (size_t)nleaf;
+    const std::string& have = ctx->prolong_cache_key;
+    fava_prolong_leaf* d_leaves;
+    int32_t* d_table;
+    if (ctx->ws[WS_TABLE] && have.size() == key_bytes && memcmp(have.data(), head, sizeof(head)) == 0 &&
+        (nleaf == 0 || memcmp(have.data() + sizeof(head), h_leaves, sizeof(fava_prolong_leaf) * (size_t)nleaf) == 0)) {
+        d_leaves = (fava_prolong_leaf*)ctx->ws[WS_TABLE];
+        d_table = (int32_t*)((char*)ctx->ws[WS_TABLE] + b_leaves);
+    } else {
+        ctx->prolong_cache_key.clear();
+        std::vector<int32_t> table((size_t)ntile, -1);
+        for (int64_t l = 0; l < nleaf; ++l) {
+            const fava_prolong_leaf& d = h_leaves[l];
+            if (d.scale < 1 || (d.scale & (d.scale - 1)) || d.block < 0)
+                return set_error(FAVA_EINVAL, "fava_prolong: leaf %lld has scale %d (must be a power of two) / block %lld",
+                                 (long long)l, d.scale, (long long)d.block);
+            if (pmod(d.off[0], nxb) != g.sx || pmod(d.off[1], nyb) != g.sy || pmod(d.off[2], nzb) != g.sz)
+                return set_error(FAVA_EINVAL, "fava_prolong: leaf %lld corner (%d,%d,%d) is not on the block lattice",
+                                 (long long)l, d.off[0], d.off[1], d.off[2]);
+            // tiles covered by the leaf, clipped to the table
+            int64_t lo[3], hi[3];
+            const int dims[3] = {g.tx, g.ty, g.tz};
+            bool empty = false;
+            for (int a = 0; a < 3; ++a) {
+                // off may be far negative: floor division
+                const int64_t nb = a == 0 ? nxb : (a == 1 ? nyb : nzb);
+                const int64_t num = (int64_t)d.off[a] - (a == 0 ? g.sx : (a == 1 ? g.sy : g.sz)) + nb;
+                const int64_t first = num >= 0 ? num / nb : -((-num + nb - 1) / nb);
+                lo[a] = std::max<int64_t>(first, 0);
+                hi[a] = std::min<int64_t>(first + d.scale, dims[a]);
+                if (hi[a] <= lo[a]) empty = true;
+            }
+            if (empty) continue;
+            for (int64_t z = lo[2]; z < hi[2]; ++z)
+                for (int64_t y = lo[1]; y < hi[1]; ++y)
+                    for (int64_t x = lo[0]; x < hi[0]; ++x) table[(size_t)((z * g.ty + y) * g.tx + x)] = (int32_t)l;
+        }
+        void* tab;
+        int rc = ctx_workspace(ctx, WS_TABLE, b_leaves + b_table, &tab);
+        if (rc) return rc;
+        d_leaves = (fava_prolong_leaf*)tab;
+        d_table = (int32_t*)((char*)tab + b_leaves);
+        if (nleaf) FAVA_CHECK_CUDA(cudaMemcpyAsync(d_leaves, h_leaves, sizeof(fava_prolong_leaf) * nleaf, cudaMemcpyHostToDevice, st));
+        FAVA_CHECK_CUDA(cudaMemcpyAsync(d_table, table.data(), b_table, cudaMemcpyHostToDevice, st));
+        std::string key(key_bytes, '\0');
+        memcpy(&key[0], head, sizeof(head));
+        if (nleaf) memcpy(&key[sizeof(head)], h_leaves, sizeof(fava_prolong_leaf) * (size_t)nleaf);
+        ctx->prolong_cache_key.swap(key);
+    }
 
-    const int64_t rows = NZ * NY;
-    const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdivp(NX, 512), 64));
-    const unsigned gy = (unsigned)std::min<int64_t>(rows, 32768);
-    const unsigned gz = (unsigned)cdivp(rows, gy);
-    k_prolong<T><<<dim3(gx, gy, gz), 256, 0, st>>>(blocks, d_leaves, d_table, g, out);
+    const unsigned gx = (unsigned)std::min<int64_t>(ntile, 65535);
+    const unsigned gy = (unsigned)cdivp(ntile, gx);
+    k_prolong<T><<<dim3(gx, gy), 256, 0, st>>>(blocks, d_leaves, d_table, g, out);
     FAVA_LAUNCHED();
     return FAVA_OK;
 }

@@ -240,7 +240,7 @@ int fava_stage_host_h2d(fava_ctx* ctx, const void* h_src, int64_t nbytes, void* 
 /* Grow-only device buffer owned by the context (a plain cudaMalloc allocation, so that it can be
  * exported with fava_ipc_export); zero-filled when (re)allocated.  Slots 8..15 are free for callers. */
 #define FAVA_WS_USER0 8
-#define FAVA_WS_NSLOTS 16
+#define FAVA_WS_NSLOTS 20
 int fava_workspace(fava_ctx* ctx, int slot, int64_t bytes, void** d_ptr_out);
 int fava_ipc_export(void* d_ptr, unsigned char handle_out[64]);
 int fava_ipc_open(const unsigned char handle[64], void** d_ptr_out);
