@@ -384,6 +384,8 @@ class FLASH(Structured):
         return ilo.astype(np.int64), scale, np.asarray(vol, dtype=np.float64)
 
     def _plane_statistics(self, axis: int, favre: bool):
+        if int(self.ndim) != 3:
+            raise NotImplementedError("fava_b200 computes plane statistics for 3-D datasets (rho, velx, vely, velz)")
         axis, n, nrb, min_delta, layer_volume, radius = self._axis_setup(axis)
         t = [self.device_data(k) for k in ("dens",) + _VEL]
         if self._part[0] == "slab":

@@ -138,7 +138,8 @@ def slab_ke_spectrum(rho, ux, uy, uz, n: int, overlap=None, epilogue=None) -> di
     kernel and before the host synchronises on the shell sums."""
     world, rank = dist.world_size(), dist.rank()
     if world == 1:
-        for hook in (overlap, epilogue):
+        hooks = list(overlap) if isinstance(overlap, (list, tuple)) else [overlap]
+        for hook in hooks + [epilogue]:
             if hook is not None:
                 hook()
         return device.ke_spectrum(rho, ux, uy, uz)
@@ -159,10 +160,16 @@ def slab_ke_spectrum(rho, ux, uy, uz, n: int, overlap=None, epilogue=None) -> di
             # passed this stream-ordered collective (each enqueues it after its own pack kernel)
             dist.allreduce_sum_(p.tokens[c])
             p.ev_done[c].record(p.comm_stream)
-    if overlap is not None:
-        overlap()
-    p.ev_mark["overlap"].record(cur)
+    # `overlap` may be one callable or a list of them: the z-transform of component c is enqueued after the
+    # c-th piece, so that it starts as soon as its exchange is done instead of queueing behind all the pieces
+    pieces = list(overlap) if isinstance(overlap, (list, tuple)) else ([overlap] if overlap is not None else [])
     for c in range(3):
+        if c < len(pieces):
+            pieces[c]()
+        if c == 2:
+            for extra in pieces[3:]:
+                extra()
+            p.ev_mark["overlap"].record(cur)
         cur.wait_event(p.ev_done[c])
         device.fft_z(p.recv[c], n, p.nyl * p.nxh, dev)
     p.ev_mark["fft_z"].record(cur)

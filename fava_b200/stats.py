@@ -96,13 +96,25 @@ def slab_step(rho, ux, uy, uz, n: int, cell_volume: float, layer_volume: float, 
 
     out, pending = {}, {}
 
-    def local_moments():
-        todo = list(axes)
-        if 0 in todo and 2 in todo:  # x and z bins from ONE pass over the slab
-            pending[0], pending[2] = device.plane_moments_xz(rho, ux, uy, uz)
-            todo = [ax for ax in todo if ax == 1]
-        for ax in todo:
+    def moments_xz():  # x and z bins from ONE pass over the slab
+        pending[0], pending[2] = device.plane_moments_xz(rho, ux, uy, uz)
+
+    def moments_of(ax):
+        def run():
             pending[ax] = slab_moments_local(rho, ux, uy, uz, ax)
+
+        return run
+
+    pieces = []
+    todo = list(axes)
+    if 0 in todo and 2 in todo:
+        pieces.append(moments_xz)
+        todo = [ax for ax in todo if ax == 1]
+    pieces += [moments_of(ax) for ax in todo]
+
+    def local_moments():
+        for piece in pieces:
+            piece()
 
     def finish_profiles():
         for ax in axes:
@@ -110,7 +122,7 @@ def slab_step(rho, ux, uy, uz, n: int, cell_volume: float, layer_volume: float, 
             out[ax] = slab_profiles_finish(mom, piv, ax, cell_volume, layer_volume, favre=favre, gather=False)
 
     if spectrum:
-        out["spectrum"] = spec.slab_ke_spectrum(rho, ux, uy, uz, n, overlap=local_moments, epilogue=finish_profiles)
+        out["spectrum"] = spec.slab_ke_spectrum(rho, ux, uy, uz, n, overlap=pieces, epilogue=finish_profiles)
     else:
         local_moments()
         finish_profiles()
