@@ -21,16 +21,17 @@ from fava_b200 import device, dist
 
 def ky_ownership(n: int, nranks: int) -> np.ndarray:
     """[nranks][nyl] global ky indices owned by each rank (-1 = padding).  Rank r owns the wavenumbers
-    |ky| in [r*h, (r+1)*h), h = N/(2P), as index pairs (j, N-j); the Nyquist row j = N/2 is owned by
-    nobody (it lies beyond the last bin edge).  nyl = 2h."""
+    |ky| = r, r + P, r + 2P, ... < N/2 (cyclic: every rank gets the same share of the spectral SPHERE, so the
+    binning work is balanced) as index pairs (j, N-j), the non-negative rows first; the Nyquist row j = N/2 is
+    owned by nobody (it lies beyond the last bin edge).  nyl = N/P."""
     if n % (2 * nranks):
         raise ValueError(f"grid size {n} must be divisible by 2 x {nranks} ranks")
     h = n // (2 * nranks)
     own = -np.ones((nranks, 2 * h), dtype=np.int32)
     for r in range(nranks):
-        pos = np.arange(r * h, (r + 1) * h)
-        neg = (n - pos) % n
-        rows = list(pos) + [j for j in neg[::-1] if j not in pos]
+        pos = np.arange(r, n // 2, nranks)
+        neg = [(n - j) % n for j in pos if j != 0]
+        rows = list(pos) + neg
         own[r, : len(rows)] = rows
     return own
 

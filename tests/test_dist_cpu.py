@@ -78,5 +78,8 @@ def test_ky_ownership_is_symmetric_and_complete(n, world):
     for r in range(world):
         rows = set(own[r][own[r] >= 0].tolist())
         assert all(((n - j) % n) in rows for j in rows)  # +-ky on the same rank
+        h = n // (2 * world)
+        assert all(0 <= j < n // 2 for j in own[r][:h])  # the non-negative wavenumbers come first
+        assert sorted(own[r][:h] % world) == [r] * h  # cyclic in |ky|: balanced share of the spectral sphere
     with pytest.raises(ValueError):
         spectrum.ky_ownership(20, 8)
