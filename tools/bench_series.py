@@ -2,7 +2,7 @@
 """BASELINE configs[4] in miniature: Reynolds-stress time series over synthetic multi-block plt files, sharded
 over the ranks, staged file -> pinned ring -> HBM.  Prints one JSON line (not the driver's bench contract).
 
-    python tools/bench_series.py [--n 512] [--block 16] [--files 4]        (torchrun for N > 1)
+    python tools/bench_series.py [--grid 512] [--block 16] [--files 4]        (torchrun for N > 1)
 """
 import argparse
 import json
@@ -19,7 +19,7 @@ sys.path.insert(0, str(ROOT))
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=512)
+    ap.add_argument("--grid", dest="n", type=int, default=512)
     ap.add_argument("--block", type=int, default=16)
     ap.add_argument("--files", type=int, default=4)
     ap.add_argument("--dir", default=None)
