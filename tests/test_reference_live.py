@@ -1,0 +1,74 @@
+"""CPU, build container only (skipped where /root/reference is absent, e.g. on the GPU box): the UNMODIFIED
+reference, run through oracle/ref_harness.py on fresh synthetic files, against the NumPy oracle — cases beyond the
+committed golden vectors (other seeds, shapes, extents, refinement patterns)."""
+import numpy as np
+import pytest
+
+from fava_b200 import synth
+from oracle import fava_oracle as orc
+from oracle import ref_harness as rh
+from tests._util import FIELDS, STRESS, oracle_data, oracle_geom
+
+pytestmark = pytest.mark.skipif(not rh.reference_available(), reason="the reference is only mounted in the build container")
+
+
+@pytest.mark.parametrize("seed,nroot,nb,levels", [(21, (2, 1, 2), (4, 8, 4), 3), (22, (1, 1, 1), (8, 8, 8), 2), (23, (3, 2, 1), (4, 4, 4), 2)])
+def test_reynolds_stress_reference_equals_oracle(tmp_path, seed, nroot, nb, levels):
+    mesh = synth.octree_mesh(nroot, nb, levels, seed=seed, p_refine=0.4, bounds=((0.0, 3.0), (-1.0, 1.0), (0.5, 1.5)))
+    fields = synth.block_fields(mesh, names=FIELDS, dtype=np.float32, seed=seed, u0=2.0)
+    p = tmp_path / "live_hdf5_plt_cnt_0000"
+    synth.write_flash_file(p, mesh, fields)
+    radius, stress, means = rh.ref_reynolds_stress(p, 0)
+    r0, s0, m0 = orc.reynolds_stress(oracle_geom(mesh), oracle_data(fields), axis=0)
+    assert np.array_equal(radius, r0)
+    for k in STRESS:
+        assert np.array_equal(stress[k], s0[k]), k
+    for k in FIELDS:
+        assert np.array_equal(means[k], m0[k]), k
+
+
+@pytest.mark.parametrize("box,level", [(np.array([[0.1, 0.9], [0.2, 0.7], [0.05, 0.95]]), -1),
+                                       (np.array([[0.5, 1.0], [0.5, 1.0], [0.5, 1.0]]), 3),
+                                       (np.array([[0.0, 1.0], [0.0, 1.0], [0.0, 1.0]]), 1)])
+def test_from_amr_reference_equals_oracle(tmp_path, box, level):
+    mesh = synth.octree_mesh((2, 2, 2), (4, 4, 4), 3, seed=31, p_refine=0.5)
+    fields = synth.block_fields(mesh, names=("dens",), dtype=np.float32, seed=31)
+    p = tmp_path / "live_hdf5_plt_cnt_0001"
+    synth.write_flash_file(p, mesh, fields)
+    m, res = rh.ref_from_amr(p, box, level, fields=("dens",), filename=tmp_path / "live_hdf5_uniform_0001")
+    geom = oracle_geom(mesh)
+    plan = orc.from_amr_plan(geom, box, level)
+    assert np.array_equal(res["dens"], orc.from_amr_gather(geom, plan, orc.load_like_reference(fields["dens"])))
+
+
+@pytest.mark.parametrize("n,seed", [(8, 41), (24, 42)])
+def test_kinetic_energy_spectra_reference_equals_oracle(tmp_path, n, seed):
+    f = synth.uniform_fields((n, n, n), names=FIELDS, dtype=np.float32, seed=seed, u0=0.3)
+    p = tmp_path / f"live_hdf5_uniform_{n:04d}"
+    synth.write_flash_file(p, synth.single_block_mesh((n, n, n)), f, uniform3d=True)
+    ref = rh.ref_kinetic_energy_spectra(p)
+    got = orc.kinetic_energy_spectra({k: orc.load_like_reference(v) for k, v in f.items()}, (n, n, n), use_scipy=False)
+    for k in ref:
+        assert np.array_equal(ref[k], got[k], equal_nan=True), k
+
+
+def test_reference_quirks_documented_in_survey(tmp_path):
+    """raxis != 0 still reduces x-planes: the "y profile" is the x profile, truncated and rescaled;
+    a non-cubic grid breaks the spectrum's `.T` projection (§0.6)."""
+    shape = (8, 12, 16)
+    f = synth.uniform_fields(shape, names=FIELDS, dtype=np.float32, seed=5)
+    mesh = synth.single_block_mesh(shape)
+    p = tmp_path / "q_hdf5_plt_cnt_0000"
+    synth.write_flash_file(p, mesh, f)
+    _, _, means_y = rh.ref_reynolds_stress(p, 1)
+    geom, data = oracle_geom(mesh), oracle_data(f)
+    _, _, true_x = orc.reynolds_stress(geom, data, axis=0)
+    _, _, true_y = orc.reynolds_stress(geom, data, axis=1)
+    assert means_y["dens"].shape == true_y["dens"].shape == (12,)
+    ratio = means_y["dens"] / true_x["dens"][:12]
+    assert np.allclose(ratio, ratio[0], rtol=1e-12)  # x-plane sums under a y label
+    assert not np.allclose(means_y["dens"], true_y["dens"], rtol=1e-6)
+    pu = tmp_path / "q_hdf5_uniform_0000"
+    synth.write_flash_file(pu, mesh, f, uniform3d=True)
+    with pytest.raises(ValueError):
+        rh.ref_kinetic_energy_spectra(pu)
