@@ -148,19 +148,33 @@ __device__ __forceinline__ int freq_to_pos(int k) {
     return p;
 }
 
-// One DIF pass of radix R on one line: butterfly jb of the line, elements at sm[line_off + skew(n) * sn].
-template <int R, int LOGN, bool SKEW>
+// Skewed position of element n in a line-major (ROWS) buffer: +1 every 8 elements, +5 every 64.  With 16-byte
+// elements a 128-byte bank row holds 8 of them; this skew makes the 8 lanes of every access phase hit 8 distinct
+// bank groups in ALL the access patterns of the x pass (stride 1, stride 64 blocks walked block-fastest,
+// stride-4 radix-4 groups, and the digit-reversed gather of the split, whose lane stride is 64) —
+// ncu had shown 54 % of the shared-memory wavefronts of the un-skewed kernel to be bank conflicts.
+__host__ __device__ __forceinline__ constexpr int skew(int n) { return n + (n >> 3) + 5 * (n >> 6); }
+
+// One DIF pass of radix R on one line: butterfly jb of the line, elements at sm[line_off + pos(n) * sn].
+// BLKFAST: consecutive jb walk the N/L blocks first (their address stride is odd in bank rows under `skew`).
+template <int R, int LOGN, bool SKEW, bool BLKFAST>
 __device__ __forceinline__ void fft_pass(double2* __restrict__ sm, int line_off, int sn, int L, int jb,
                                          const double2* __restrict__ tw, bool twiddle) {
     constexpr int N = 1 << LOGN;
     const int per = L / R;
-    const int blk = jb / per, j = jb - blk * per;
+    int blk, j;
+    if (BLKFAST) {
+        const int nblk = N / L;
+        j = jb / nblk, blk = jb - j * nblk;
+    } else {
+        blk = jb / per, j = jb - blk * per;
+    }
     const int base = blk * L + j;
     double2 v[R];
 #pragma unroll
     for (int m = 0; m < R; ++m) {
         const int n = base + m * per;
-        v[m] = sm[line_off + (SKEW ? n + (n >> 6) : n) * sn];
+        v[m] = sm[line_off + (SKEW ? skew(n) : n) * sn];
     }
     dft<R>(v);
     if (twiddle) {
@@ -171,7 +185,7 @@ __device__ __forceinline__ void fft_pass(double2* __restrict__ sm, int line_off,
 #pragma unroll
     for (int q = 0; q < R; ++q) {
         const int n = base + q * per;
-        sm[line_off + (SKEW ? n + (n >> 6) : n) * sn] = v[q];
+        sm[line_off + (SKEW ? skew(n) : n) * sn] = v[q];
     }
 }
 
@@ -194,10 +208,18 @@ __device__ __forceinline__ void fft_lines_smem(double2* __restrict__ sm, int nli
             else jb = item % nb, c = item / nb;
             const int off = COLS ? c : c * pitch;
             const int sn = COLS ? nlines : 1;
-            if (r == 16) fft_pass<16, LOGN, !COLS>(sm, off, sn, L, jb, tw, twd);
-            else if (r == 8) fft_pass<8, LOGN, !COLS>(sm, off, sn, L, jb, tw, twd);
-            else if (r == 4) fft_pass<4, LOGN, !COLS>(sm, off, sn, L, jb, tw, twd);
-            else fft_pass<2, LOGN, !COLS>(sm, off, sn, L, jb, tw, twd);
+            // ROWS layout: the first pass walks butterflies j-fastest (stride 1), later passes block-fastest
+            if (COLS || s == 0) {
+                if (r == 16) fft_pass<16, LOGN, !COLS, false>(sm, off, sn, L, jb, tw, twd);
+                else if (r == 8) fft_pass<8, LOGN, !COLS, false>(sm, off, sn, L, jb, tw, twd);
+                else if (r == 4) fft_pass<4, LOGN, !COLS, false>(sm, off, sn, L, jb, tw, twd);
+                else fft_pass<2, LOGN, !COLS, false>(sm, off, sn, L, jb, tw, twd);
+            } else {
+                if (r == 16) fft_pass<16, LOGN, !COLS, true>(sm, off, sn, L, jb, tw, twd);
+                else if (r == 8) fft_pass<8, LOGN, !COLS, true>(sm, off, sn, L, jb, tw, twd);
+                else if (r == 4) fft_pass<4, LOGN, !COLS, true>(sm, off, sn, L, jb, tw, twd);
+                else fft_pass<2, LOGN, !COLS, true>(sm, off, sn, L, jb, tw, twd);
+            }
         }
         __syncthreads();
         L /= r;
@@ -213,26 +235,23 @@ __global__ void __launch_bounds__(kFftThreads, 2)
                    const T* __restrict__ uz, int64_t nrows, const double2* __restrict__ tw, double2* __restrict__ fx,
                    double2* __restrict__ fy, double2* __restrict__ fz) {
     constexpr int N = 1 << LOGN, NH = N / 2 + 1;
-    constexpr int PITCH = N + (N >> 6) + 1;  // skewed line + 1
+    constexpr int PITCH = skew(N - 1) + 2;  // skewed line length, padded
     extern __shared__ __align__(16) unsigned char fft_smem[];
     double2* sm = reinterpret_cast<double2*>(fft_smem);  // [3][PITCH]
     const int64_t r0 = (int64_t)blockIdx.x * 2;
     const bool two = r0 + 1 < nrows;
     const T* u[3] = {ux, uy, uz};
-    // z_c[n] = w_c[r0][n] + i w_c[r0+1][n],  w = sqrt(rho) u
-    for (int n = threadIdx.x * 2; n < N; n += kFftThreads * 2) {
-        double ra[2], rb[2] = {0.0, 0.0};
-        VecLoad<T, 2>::ld(rho + r0 * N + n, ra);
-        if (two) VecLoad<T, 2>::ld(rho + (r0 + 1) * N + n, rb);
-        const double sa0 = sqrt(ra[0]), sa1 = sqrt(ra[1]), sb0 = sqrt(rb[0]), sb1 = sqrt(rb[1]);
+    // z_c[n] = w_c[r0][n] + i w_c[r0+1][n],  w = sqrt(rho) u; lane <-> n: coalesced loads, conflict-free stores
+    for (int n = threadIdx.x; n < N; n += kFftThreads) {
+        const double ra = (double)__ldcs(rho + r0 * N + n);
+        const double rb = two ? (double)__ldcs(rho + (r0 + 1) * N + n) : 0.0;
+        const double sa = sqrt(ra), sb = sqrt(rb);
+        const int p = skew(n);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            double a[2], b[2] = {0.0, 0.0};
-            VecLoad<T, 2>::ld(u[c] + r0 * N + n, a);
-            if (two) VecLoad<T, 2>::ld(u[c] + (r0 + 1) * N + n, b);
-            const int p0 = n + (n >> 6), p1 = (n + 1) + ((n + 1) >> 6);
-            sm[c * PITCH + p0] = make_double2(sa0 * a[0], sb0 * b[0]);
-            sm[c * PITCH + p1] = make_double2(sa1 * a[1], sb1 * b[1]);
+            const double a = (double)__ldcs(u[c] + r0 * N + n);
+            const double b = two ? (double)__ldcs(u[c] + (r0 + 1) * N + n) : 0.0;
+            sm[c * PITCH + p] = make_double2(sa * a, sb * b);
         }
     }
     __syncthreads();
@@ -240,8 +259,7 @@ __global__ void __launch_bounds__(kFftThreads, 2)
     // split: row r0 gets (Z[k] + conj Z[N-k]) / 2, row r0+1 gets (Z[k] - conj Z[N-k]) / (2i)
     double2* out[3] = {fx, fy, fz};
     for (int k = threadIdx.x; k < NH; k += kFftThreads) {
-        const int pa = freq_to_pos<LOGN>(k), pb = freq_to_pos<LOGN>((N - k) & (N - 1));
-        const int ia = pa + (pa >> 6), ib = pb + (pb >> 6);
+        const int ia = skew(freq_to_pos<LOGN>(k)), ib = skew(freq_to_pos<LOGN>((N - k) & (N - 1)));
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const double2 A = sm[c * PITCH + ia], B = sm[c * PITCH + ib];
@@ -255,8 +273,8 @@ __global__ void __launch_bounds__(kFftThreads, 2)
 
 // ---- strided column pass ------------------------------------------------------------------------------------
 // data: complex [nbatch][N][ncols]; transform along the middle axis for every (batch, column).
-template <int LOGN, int C>
-__global__ void __launch_bounds__(kFftThreads)
+template <int LOGN, int C, int THREADS>
+__global__ void __launch_bounds__(THREADS)
     k_fft_cols(double2* __restrict__ data, int64_t ncols, int64_t ntiles_per_batch, const double2* __restrict__ tw,
                int prune_kmax2, int prune_nxh, int prune_n, const int32_t* __restrict__ ky_of_local, int debug_nopass) {
     constexpr int N = 1 << LOGN;
@@ -282,19 +300,19 @@ __global__ void __launch_bounds__(kFftThreads)
     }
     double2* base = data + batch * (int64_t)N * ncols + c0;
     if (nc == C) {
-        for (int item = threadIdx.x; item < N * C; item += kFftThreads) {
+        for (int item = threadIdx.x; item < N * C; item += THREADS) {
             const int c = item % C, n = item / C;
             sm[item] = __ldcs(base + (int64_t)n * ncols + c);
         }
     } else {
-        for (int item = threadIdx.x; item < N * C; item += kFftThreads) {
+        for (int item = threadIdx.x; item < N * C; item += THREADS) {
             const int c = item % C, n = item / C;
             sm[item] = c < nc ? __ldcs(base + (int64_t)n * ncols + c) : make_double2(0.0, 0.0);
         }
     }
     __syncthreads();
     if (!debug_nopass) fft_lines_smem<LOGN, true>(sm, C, 0, tw);
-    for (int item = threadIdx.x; item < N * C; item += kFftThreads) {
+    for (int item = threadIdx.x; item < N * C; item += THREADS) {
         const int c = item % C, p = item / C;
         if (c < nc) base[(int64_t)pos_to_freq<LOGN>(p) * ncols + c] = sm[item];
     }
@@ -342,7 +360,7 @@ template <typename T, int LOGN>
 static int launch_x(const T* rho, const T* ux, const T* uy, const T* uz, int64_t nrows, const double2* tw, double2* fx,
                     double2* fy, double2* fz, cudaStream_t st) {
     constexpr int N = 1 << LOGN;
-    const size_t smem = sizeof(double2) * 3 * (N + (N >> 6) + 1);
+    const size_t smem = sizeof(double2) * 3 * (skew(N - 1) + 2);
     FAVA_CHECK_CUDA(cudaFuncSetAttribute(k_fft_x_weight<T, LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_fft_x_weight<T, LOGN><<<(unsigned)((nrows + 1) / 2), kFftThreads, smem, st>>>(rho, ux, uy, uz, nrows, tw, fx, fy, fz);
     FAVA_LAUNCHED();
@@ -356,9 +374,10 @@ static int launch_cols_c(double2* data, int64_t ncols, int64_t nbatch, const dou
     const size_t smem = sizeof(double2) * (size_t)N * C;
     const int64_t tiles = (ncols + C - 1) / C;
     if (tiles * nbatch > 0x7fffffffLL) return set_error(FAVA_EINVAL, "fft_cols: too many tiles");
-    FAVA_CHECK_CUDA(cudaFuncSetAttribute(k_fft_cols<LOGN, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    constexpr int THREADS = (N / 16) * C < 256 ? 256 : ((N / 16) * C > 1024 ? 1024 : (N / 16) * C);
+    FAVA_CHECK_CUDA(cudaFuncSetAttribute(k_fft_cols<LOGN, C, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const char* e = getenv("FAVA_FFT_DEBUG_NOPASS");
-    k_fft_cols<LOGN, C><<<(unsigned)(tiles * nbatch), kFftThreads, smem, st>>>(data, ncols, tiles, tw, kmax2, nxh, n,
+    k_fft_cols<LOGN, C, THREADS><<<(unsigned)(tiles * nbatch), THREADS, smem, st>>>(data, ncols, tiles, tw, kmax2, nxh, n,
                                                                              ky_of_local, e ? atoi(e) : 0);
     FAVA_LAUNCHED();
     return FAVA_OK;
