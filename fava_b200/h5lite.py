@@ -4,7 +4,8 @@ What FLASH (and FAVA's own writer, reference fava/mesh/FLASH/_flash.py:619-799) 
 classic on-disk format: superblock v0/v1, groups as symbol tables (B-tree v1 + local heap + SNOD),
 version-1 object headers, and datasets with a simple dataspace, a fixed-point / float / fixed-string
 / compound datatype and a CONTIGUOUS (or compact) layout.  That is all this module reads and writes;
-anything else (chunked or filtered datasets, new-style groups, variable-length types) fails loudly.
+nested groups included (the analysis-result files of fava/model/model.py:138-185); anything else (chunked or
+filtered datasets, new-style groups, variable-length types) fails loudly.
 
 Two faces:
   * an h5py-shaped facade — `File`, `Group`, `Dataset` with `shape/dtype/nbytes`, `d[()]`,
@@ -354,6 +355,12 @@ class Group:
         return key in self._entries
 
     def __getitem__(self, key: str):
+        parts = [q for q in str(key).split("/") if q]
+        if len(parts) > 1:
+            node = self
+            for part in parts:
+                node = node[part]
+            return node
         if key not in self._entries:
             raise KeyError(f"Unable to open object (object {key!r} doesn't exist)")
         ohdr, cache, scratch = self._entries[key]
@@ -397,20 +404,90 @@ def _normalise_dtype(dtype) -> np.dtype:
     return np.dtype(dtype)
 
 
+def _as_array(shape, dtype, data) -> np.ndarray:
+    dt = _normalise_dtype(dtype) if dtype is not None else None
+    if data is None:
+        if shape is None:
+            raise TypeError("One of data, shape or dtype must be specified")
+        shp = (int(shape),) if np.isscalar(shape) else tuple(int(s) for s in shape)
+        return np.zeros(shp, dtype=dt if dt is not None else np.float32)
+    arr = np.asarray(data) if dt is None else np.asarray(data, dtype=dt)
+    if shape is not None:
+        shp = (int(shape),) if np.isscalar(shape) else tuple(int(s) for s in shape)
+        if int(np.prod(shp, dtype=np.int64)) != arr.size:
+            raise ValueError(f"Shape tuple is incompatible with data ({shp} vs {arr.shape})")
+        arr = arr.reshape(shp)
+    if arr.dtype.kind == "U":
+        arr = arr.astype("S")
+    if arr.dtype.kind == "O":
+        raise H5LiteError("object arrays cannot be stored")
+    if arr.dtype.kind == "b":
+        arr = arr.astype(np.int8)
+    return arr
+
+
+class WGroup:
+    """A group of a file open for writing ("w" or "a"): an in-memory tree written out on close.  Offers the h5py
+    calls the reference's writers make: create_dataset, create_group (raises if the name exists —
+    fava/model/model.py:155-158 relies on that), [], in, keys(), del."""
+
+    def __init__(self, name: str = "/"):
+        self.name = name
+        self.items: dict[str, "WGroup | _PendingDataset"] = {}
+
+    def keys(self):
+        return self.items.keys()
+
+    def __iter__(self):
+        return iter(self.items)
+
+    def __len__(self):
+        return len(self.items)
+
+    def __contains__(self, key) -> bool:
+        return key in self.items
+
+    def __getitem__(self, key: str):
+        node = self
+        for part in [q for q in str(key).split("/") if q]:
+            if not isinstance(node, WGroup) or part not in node.items:
+                raise KeyError(f"Unable to open object (object {key!r} doesn't exist)")
+            node = node.items[part]
+        return node
+
+    def __delitem__(self, key: str) -> None:
+        if key not in self.items:
+            raise KeyError(f"Couldn't delete link (name {key!r} doesn't exist)")
+        del self.items[key]
+
+    def create_group(self, name: str) -> "WGroup":
+        if name in self.items:
+            raise ValueError(f"Unable to create group (name already exists): {name!r}")
+        g = WGroup(name)
+        self.items[name] = g
+        return g
+
+    def create_dataset(self, name: str, shape=None, dtype=None, data=None, **_kw):
+        if name in self.items:
+            raise ValueError(f"Unable to create dataset (name already exists): {name!r}")
+        ds = _PendingDataset(name, _as_array(shape, dtype, data))
+        self.items[name] = ds
+        return ds
+
+
 class _Writer:
+    """Serialises a WGroup tree: per group an object header (symbol-table message), one B-tree leaf-level node, a
+    local heap and symbol-table nodes; per dataset an object header; then the raw data (large datasets page-aligned)."""
+
     LEAF_K = 4
     INTERNAL_K = 16
 
-    def __init__(self, path: Path):
+    def __init__(self, path: Path, root: WGroup | None = None):
         self.path = Path(path)
-        self.items: dict[str, _PendingDataset] = {}
+        self.root = root if root is not None else WGroup()
 
-    def add(self, name: str, arr: np.ndarray):
-        if name in self.items:
-            raise ValueError(f"Unable to create dataset (name already exists): {name!r}")
-        self.items[name] = _PendingDataset(name, arr)
-
-    def _dataset_header(self, ds: _PendingDataset, addr: int) -> bytes:
+    @staticmethod
+    def _dataset_header(ds: _PendingDataset, addr: int) -> bytes:
         rank = len(ds.shape)
         msgs = []
         space = struct.pack("<BBBBI", 1, rank, 0, 0, 0) + struct.pack(f"<{rank}Q", *ds.shape)
@@ -425,91 +502,120 @@ class _Writer:
         return struct.pack("<BBHII4x", 1, 0, len(msgs), 1, len(body)) + body
 
     def flush(self):
-        names = sorted(self.items, key=lambda s: s.encode())
         per = 2 * self.LEAF_K
-        groups = [names[i : i + per] for i in range(0, len(names), per)] or [[]]
-        if len(groups) > 2 * self.INTERNAL_K:
-            raise H5LiteError(f"too many objects in one group for h5lite ({len(names)})")
-        # local heap data: "" at 0, then names
-        heap = bytearray(8)
-        name_off = {}
-        for n in names:
-            name_off[n] = len(heap)
-            b = n.encode() + b"\0"
-            heap += b + b"\0" * (_pad8(len(b)) - len(b))
-        # layout of metadata
+        btree_bytes = 24 + (2 * 2 * self.INTERNAL_K + 1) * 8
         pos = 96  # superblock
-        root_ohdr = pos
-        pos += 16 + 24  # header + one symbol-table message
-        btree_addr = pos
-        pos += 24 + (2 * 2 * self.INTERNAL_K + 1) * 8
-        heap_addr = pos
-        pos += 32
-        heap_data = pos
-        pos += len(heap)
-        snod_addr = []
-        for _ in groups:
-            snod_addr.append(pos)
-            pos += 8 + per * 40
-        ohdr_addr = {}
-        ohdr_len = {}
-        for n in names:
-            ohdr_addr[n] = pos
-            ohdr_len[n] = len(self._dataset_header(self.items[n], 0))
-            pos += ohdr_len[n]
+        plans = []  # (group, layout dict) in allocation order
+        datasets = []  # (dataset, object-header address)
+
+        def plan_group(g: WGroup) -> dict:
+            nonlocal pos
+            names = sorted(g.items, key=lambda q: q.encode())
+            chunks = [names[i : i + per] for i in range(0, len(names), per)] or [[]]
+            if len(chunks) > 2 * self.INTERNAL_K:
+                raise H5LiteError(f"too many objects in one group for h5lite ({len(names)})")
+            heap = bytearray(8)  # "" at offset 0
+            name_off = {}
+            for n in names:
+                name_off[n] = len(heap)
+                b = n.encode() + b"\0"
+                heap += b + b"\0" * (_pad8(len(b)) - len(b))
+            lay = {"names": names, "chunks": chunks, "heap": bytes(heap), "name_off": name_off}
+            lay["ohdr"] = pos
+            pos += 16 + 24
+            lay["btree"] = pos
+            pos += btree_bytes
+            lay["heap_addr"] = pos
+            pos += 32
+            lay["heap_data"] = pos
+            pos += len(heap)
+            lay["snod"] = []
+            for _ in chunks:
+                lay["snod"].append(pos)
+                pos += 8 + per * 40
+            plans.append((g, lay))
+            lay["child"] = {}
+            for n in names:
+                node = g.items[n]
+                if isinstance(node, WGroup):
+                    lay["child"][n] = plan_group(node)
+                else:
+                    lay["child"][n] = pos
+                    datasets.append((node, pos))
+                    pos += len(self._dataset_header(node, 0))
+            return lay
+
+        root_lay = plan_group(self.root)
         data_addr = {}
-        for n in names:
-            nb = self.items[n].nbytes
+        for ds, _ in datasets:
+            nb = ds.nbytes
             align = DATA_ALIGN if nb >= _SMALL else 8
             pos = (pos + align - 1) // align * align
-            data_addr[n] = pos
+            data_addr[id(ds)] = pos
             pos += nb
         eof = pos
 
         with open(self.path, "wb") as f:
             sb = SIGNATURE + struct.pack("<BBBBBBBBHHI", 0, 0, 0, 0, 0, 8, 8, 0, self.LEAF_K, self.INTERNAL_K, 0)
             sb += struct.pack("<4Q", 0, UNDEF, eof, UNDEF)
-            sb += struct.pack("<QQII2Q", 0, root_ohdr, 1, 0, btree_addr, heap_addr)
+            sb += struct.pack("<QQII2Q", 0, root_lay["ohdr"], 1, 0, root_lay["btree"], root_lay["heap_addr"])
             assert len(sb) == 96
             f.write(sb)
-            stab = struct.pack("<HHB3x2Q", 0x0011, 16, 0, btree_addr, heap_addr)
-            f.write(struct.pack("<BBHII4x", 1, 0, 1, 1, len(stab)) + stab)
-            # B-tree leaf-level node
-            used = len(groups) if names else 0
-            node = b"TREE" + struct.pack("<BBHQQ", 0, 0, used, UNDEF, UNDEF)
-            keys = [0] + [name_off[g[-1]] for g in groups if g]
-            body = b""
-            for i in range(used):
-                body += struct.pack("<QQ", keys[i], snod_addr[i])
-            body += struct.pack("<Q", keys[used] if names else 0)
-            node += body
-            node += b"\0" * (24 + (2 * 2 * self.INTERNAL_K + 1) * 8 - len(node))
-            f.write(node)
-            f.write(b"HEAP" + struct.pack("<B3xQQQ", 0, len(heap), 1, heap_data))
-            f.write(bytes(heap))
-            for g, addr in zip(groups, snod_addr):
-                assert f.tell() == addr
-                blk = b"SNOD" + struct.pack("<BBH", 1, 0, len(g))
-                for n in g:
-                    blk += struct.pack("<QQII16x", name_off[n], ohdr_addr[n], 0, 0)
-                blk += b"\0" * (8 + per * 40 - len(blk))
-                f.write(blk)
-            for n in names:
-                assert f.tell() == ohdr_addr[n]
-                f.write(self._dataset_header(self.items[n], data_addr[n]))
-            for n in names:
-                arr = self.items[n].data
+            for g, lay in plans:
+                f.seek(lay["ohdr"])
+                stab = struct.pack("<HHB3x2Q", 0x0011, 16, 0, lay["btree"], lay["heap_addr"])
+                f.write(struct.pack("<BBHII4x", 1, 0, 1, 1, len(stab)) + stab)
+                names, chunks = lay["names"], lay["chunks"]
+                used = len(chunks) if names else 0
+                node = b"TREE" + struct.pack("<BBHQQ", 0, 0, used, UNDEF, UNDEF)
+                keys = [0] + [lay["name_off"][c[-1]] for c in chunks if c]
+                for i in range(used):
+                    node += struct.pack("<QQ", keys[i], lay["snod"][i])
+                node += struct.pack("<Q", keys[used] if names else 0)
+                node += b"\0" * (btree_bytes - len(node))
+                f.seek(lay["btree"])
+                f.write(node)
+                f.write(b"HEAP" + struct.pack("<B3xQQQ", 0, len(lay["heap"]), 1, lay["heap_data"]))
+                f.write(lay["heap"])
+                for c, addr in zip(chunks, lay["snod"]):
+                    blk = b"SNOD" + struct.pack("<BBH", 1, 0, len(c))
+                    for n in c:
+                        child = lay["child"][n]
+                        if isinstance(child, dict):  # sub-group: cache type 1, scratch = (B-tree, heap)
+                            blk += struct.pack("<QQII2Q", lay["name_off"][n], child["ohdr"], 1, 0, child["btree"],
+                                               child["heap_addr"])
+                        else:
+                            blk += struct.pack("<QQII16x", lay["name_off"][n], child, 0, 0)
+                    blk += b"\0" * (8 + per * 40 - len(blk))
+                    f.seek(addr)
+                    f.write(blk)
+            for ds, addr in datasets:
+                f.seek(addr)
+                f.write(self._dataset_header(ds, data_addr[id(ds)]))
+            for ds, _ in datasets:
+                arr = ds.data
                 if arr.nbytes == 0:
                     continue
-                f.seek(data_addr[n])
+                f.seek(data_addr[id(ds)])
                 flat = np.ascontiguousarray(arr)
-                mv = memoryview(flat).cast("B") if flat.dtype.fields is None and flat.dtype.kind != "S" else flat.tobytes()
-                f.write(mv)
+                plain = flat.dtype.fields is None and flat.dtype.kind != "S" and flat.ndim > 0
+                f.write(memoryview(flat).cast("B") if plain else flat.tobytes())
             f.truncate(eof)
 
 
+def _load_tree(group: "Group", out: WGroup) -> WGroup:
+    """Read a whole file into a WGroup tree (mode "a": small result files are re-written on close)."""
+    for key in group.keys():
+        node = group[key]
+        if isinstance(node, Group):
+            _load_tree(node, out.create_group(key))
+        else:
+            out.items[key] = _PendingDataset(key, node[()] if node.shape else np.asarray(node._raw()))
+    return out
+
+
 class File:
-    """h5py.File look-alike: File(name, mode) with mode "r" or "w" (context manager)."""
+    """h5py.File look-alike: File(name, mode) with mode "r", "w" or "a" (context manager)."""
 
     def __init__(self, name, mode: str = "r", **_kw):
         self.filename = str(name)
@@ -519,18 +625,33 @@ class File:
         self._root = None
         if mode == "r":
             self._reader = _Reader(Path(name))
-            if self._reader.root_scratch is not None:
-                bt, hp = self._reader.root_scratch
-            else:
-                bt, hp = self._reader.group_tables(self._reader.root_ohdr)
-            self._root = Group(self._reader, "/", bt, hp)
+            self._root = self._read_root()
         elif mode in ("w", "w-", "x"):
             if mode != "w" and Path(name).exists():
                 raise FileExistsError(name)
             self._writer = _Writer(Path(name))
             Path(name).touch()
+            self._root = self._writer.root
+        elif mode in ("a", "r+"):
+            tree = WGroup()
+            if Path(name).is_file() and Path(name).stat().st_size > 0:
+                self._reader = _Reader(Path(name))
+                _load_tree(self._read_root(), tree)
+                self._reader.close()
+                self._reader = None
+            elif mode == "r+":
+                raise FileNotFoundError(name)
+            self._writer = _Writer(Path(name), tree)
+            self._root = tree
         else:
-            raise H5LiteError(f"h5lite.File mode {mode!r} is not supported (use 'r' or 'w')")
+            raise H5LiteError(f"h5lite.File mode {mode!r} is not supported (use 'r', 'w' or 'a')")
+
+    def _read_root(self) -> "Group":
+        if self._reader.root_scratch is not None:
+            bt, hp = self._reader.root_scratch
+        else:
+            bt, hp = self._reader.group_tables(self._reader.root_ohdr)
+        return Group(self._reader, "/", bt, hp)
 
     # context manager / lifetime
     def __enter__(self):
@@ -555,48 +676,36 @@ class File:
         except Exception:
             pass
 
-    # group protocol
+    # group protocol (delegated to the root group)
     def keys(self):
-        return self._root.keys() if self._root is not None else self._writer.items.keys()
+        return self._root.keys()
 
     def __iter__(self):
-        return iter(self.keys())
+        return iter(self._root.keys())
+
+    def __len__(self):
+        return len(self._root)
 
     def __contains__(self, key) -> bool:
-        return key in self.keys()
+        return key in self._root
 
     def __getitem__(self, key: str):
-        if self._root is not None:
-            return self._root[key]
-        if key not in self._writer.items:
-            raise KeyError(f"Unable to open object (object {key!r} doesn't exist)")
-        return self._writer.items[key]
+        return self._root[key]
 
-    def create_dataset(self, name: str, shape=None, dtype=None, data=None, **_kw):
+    def __delitem__(self, key: str) -> None:
         if self._writer is None:
             raise H5LiteError("file is not open for writing")
-        dt = _normalise_dtype(dtype) if dtype is not None else None
-        if data is None:
-            if shape is None:
-                raise TypeError("One of data, shape or dtype must be specified")
-            shp = (int(shape),) if np.isscalar(shape) else tuple(int(s) for s in shape)
-            arr = np.zeros(shp, dtype=dt if dt is not None else np.float32)
-        else:
-            arr = np.asarray(data) if dt is None else np.asarray(data, dtype=dt)
-            if shape is not None:
-                shp = (int(shape),) if np.isscalar(shape) else tuple(int(s) for s in shape)
-                if int(np.prod(shp, dtype=np.int64)) != arr.size:
-                    raise ValueError(f"Shape tuple is incompatible with data ({shp} vs {arr.shape})")
-                arr = arr.reshape(shp)
-        if arr.dtype.kind == "U":
-            arr = arr.astype("S")
-        if arr.dtype.kind == "O":
-            raise H5LiteError("object arrays cannot be stored")
-        self._writer.add(name, arr)
-        return self._writer.items[name]
+        del self._root[key]
+
+    def create_dataset(self, name: str, shape=None, dtype=None, data=None, **kw):
+        if self._writer is None:
+            raise H5LiteError("file is not open for writing")
+        return self._root.create_dataset(name, shape=shape, dtype=dtype, data=data, **kw)
 
     def create_group(self, name: str):
-        raise H5LiteError("nested groups are outside h5lite's FLASH subset")
+        if self._writer is None:
+            raise H5LiteError("file is not open for writing")
+        return self._root.create_group(name)
 
 
 def is_hdf5(path) -> bool:

@@ -80,6 +80,46 @@ class Model:
         return decorator
 
 
+    # ---- analysis-result files (reference model.py:138-193) ------------------------------------------
+    def save_to_hdf5(self, data: dict, filename) -> None:
+        """Write a (nested) dict of arrays / scalars to an HDF5 file: dicts become groups, leaves datasets;
+        an existing file is opened in append mode and existing datasets are replaced."""
+        from fava_b200 import h5lite
+
+        path = Path(filename)
+        with h5lite.File(str(path), "a" if path.is_file() else "w") as f:
+            self.write_to_hdf5(f, data)
+
+    def write_to_hdf5(self, handle, data: dict) -> None:
+        import numpy as np
+
+        for key, values in data.items():
+            if isinstance(values, dict):
+                try:
+                    group = handle.create_group(key)
+                except ValueError:  # the group exists already (append)
+                    group = handle[key]
+                self.write_to_hdf5(group, values)
+                continue
+            try:
+                if key in handle.keys():
+                    del handle[key]
+                handle.create_dataset(key, data=np.copy(values))
+            except Exception as exc:  # the reference reports and carries on (model.py:176-185)
+                if dist.is_root():
+                    print(exc)
+                    print(f"[ERROR] in making {key} for {handle}", flush=True)
+
+    def hdf5_key_exists(self, key: str, filename) -> bool:
+        from fava_b200 import h5lite
+
+        path = Path(filename)
+        if not path.is_file():
+            return False
+        with h5lite.File(str(path), "r") as f:
+            return key in list(f.keys())
+
+
 class FileType(Enum):
     CHK = 0
     PLT = 1

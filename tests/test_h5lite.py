@@ -63,12 +63,57 @@ def test_rejects_non_hdf5_and_unsupported(tmp_path):
     with pytest.raises(h5lite.H5LiteError):
         h5lite.File(p, "r")
     with pytest.raises(h5lite.H5LiteError):
-        h5lite.File(tmp_path / "x", "a")
+        h5lite.File(tmp_path / "x", "q")
+    with pytest.raises(FileNotFoundError):
+        h5lite.File(tmp_path / "absent", "r+")
     with h5lite.File(tmp_path / "y", "w") as f:
         with pytest.raises(h5lite.H5LiteError):
-            f.create_group("g")
-        with pytest.raises(h5lite.H5LiteError):
             f.create_dataset("o", data=np.array([object()], dtype=object))
+    with h5lite.File(tmp_path / "y", "r") as f:
+        with pytest.raises(h5lite.H5LiteError):
+            f.create_dataset("z", data=np.zeros(3))
+
+
+def test_nested_groups_append_and_delete(tmp_path):
+    """The analysis-result files of the reference (fava/model/model.py:138-185): nested groups, scalar datasets,
+    append mode, overwrite by delete + create."""
+    p = tmp_path / "res_hdf5_analysis_0000"
+    with h5lite.File(p, "w") as f:
+        g = f.create_group("reynolds stresses")
+        t = g.create_group("tensor")
+        t.create_dataset("Rxx", data=np.arange(5.0))
+        t.create_dataset("Rxy", data=np.arange(5.0) * 2)
+        g.create_dataset("radius", data=np.linspace(0, 1, 6))
+        with pytest.raises(ValueError):
+            f.create_group("reynolds stresses")  # the reference catches this and re-opens the group
+        assert "tensor" in f["reynolds stresses"] and list(f["reynolds stresses"]["tensor"].keys()) == ["Rxx", "Rxy"]
+    with h5lite.File(p, "a") as f:  # append: scalars group, overwrite one dataset
+        s = f.create_group("scalars")
+        s.create_dataset("time", data=0.125)
+        s.create_dataset("window dimensions", data=np.array([3, 4, 5]))
+        t = f["reynolds stresses"]["tensor"]
+        del t["Rxy"]
+        t.create_dataset("Rxy", data=np.ones(5))
+        with pytest.raises(KeyError):
+            del t["nope"]
+    with h5lite.File(p, "r") as f:
+        assert sorted(f.keys()) == ["reynolds stresses", "scalars"]
+        assert np.array_equal(f["reynolds stresses"]["tensor"]["Rxx"][()], np.arange(5.0))
+        assert np.array_equal(f["reynolds stresses/tensor/Rxy"][()], np.ones(5))
+        assert np.array_equal(f["reynolds stresses"]["radius"][()], np.linspace(0, 1, 6))
+        tm = f["scalars"]["time"]
+        assert tm.shape == () and float(tm[()]) == 0.125
+        assert f["scalars"]["window dimensions"][()].tolist() == [3, 4, 5]
+    # 20 sub-groups with 12 datasets each: several symbol-table nodes per group, recursion
+    q = tmp_path / "many"
+    with h5lite.File(q, "w") as f:
+        for i in range(20):
+            g = f.create_group(f"g{i:02d}")
+            for j in range(12):
+                g.create_dataset(f"d{j:02d}", data=np.full(j + 1, i * 100 + j, dtype=np.int32))
+    with h5lite.File(q) as f:
+        assert len(list(f.keys())) == 20
+        assert f["g13"]["d07"][()].tolist() == [1307] * 8
 
 
 def test_synthetic_flash_file_schema(tmp_path):

@@ -72,3 +72,47 @@ def test_reference_quirks_documented_in_survey(tmp_path):
     synth.write_flash_file(pu, mesh, f, uniform3d=True)
     with pytest.raises(ValueError):
         rh.ref_kinetic_energy_spectra(pu)
+
+
+def test_result_writer_matches_reference_writer(tmp_path):
+    """§8f rank 2: Model.save_to_hdf5 (nested dict -> groups/datasets, append + overwrite) — the reference's own
+    writer (fava/model/model.py:138-185, running on the h5lite shim) and ours produce the same tree."""
+    import fava_b200
+    from fava_b200 import h5lite
+
+    _, _, ref_fava = rh.ref_modules()
+    (tmp_path / "run").mkdir()
+    (tmp_path / "run" / "dummy").write_text("x")
+    first = {"reynolds stresses": {"tensor": {"Rxx": np.arange(4.0), "Rxy": np.ones(4)}, "radius": np.linspace(0, 1, 5),
+                                   "means": {"dens": np.full(4, 2.0)}}}
+    second = {"scalars": {"time": 0.25, "window left": np.array([0.0, 0.1, 0.2]), "window dimensions": np.array([8, 8, 8])},
+              "reynolds stresses": {"tensor": {"Rxy": np.zeros(4)}}}
+
+    def dump(group):
+        out = {}
+        for k in group.keys():
+            node = group[k]
+            out[k] = dump(node) if hasattr(node, "keys") else np.asarray(node[()])
+        return out
+
+    trees = []
+    for mod, name in ((ref_fava, "ref"), (fava_b200, "ours")):
+        m = mod.Model(tmp_path / "run")
+        fn = tmp_path / f"{name}_hdf5_analysis_0000"
+        m.save_to_hdf5(first, fn)
+        m.save_to_hdf5(second, fn)  # append; replaces tensor/Rxy
+        assert m.hdf5_key_exists("scalars", fn) and not m.hdf5_key_exists("nope", fn)
+        with h5lite.File(fn) as f:
+            trees.append(dump(f))
+
+    def same(a, b):
+        assert sorted(a) == sorted(b)
+        for k in a:
+            if isinstance(a[k], dict):
+                same(a[k], b[k])
+            else:
+                assert a[k].dtype == b[k].dtype and a[k].shape == b[k].shape and np.array_equal(a[k], b[k]), k
+
+    same(trees[0], trees[1])
+    assert np.array_equal(trees[1]["reynolds stresses"]["tensor"]["Rxy"], np.zeros(4))
+    assert float(trees[1]["scalars"]["time"]) == 0.25
