@@ -436,6 +436,26 @@ class FLASH(Structured):
         span, alp = self.slice_integral(field, axis=ax)
         return span, alp / layer_volume
 
+    @timer
+    def flame_window(self, radius: np.ndarray, stress: dict, mask=None) -> float:
+        """Centre of the flame brush: Levenberg-Marquardt fit of a super-Gaussian amp*exp(-2((x-x0)/sigma)^10) to
+        Ryy + Rzz over the masked cells (host-side SciPy; reference _flash.py:1613-1659, same scalings)."""
+        import scipy.optimize
+
+        def super_gaussian(x, amp, x0, sigma):
+            return amp * np.exp(-2 * ((x - x0) / sigma) ** 10)
+
+        ma = mask if mask is not None else np.where(radius < np.inf)[0]
+        xfact = 1.0e5
+        rspan = radius[ma] / xfact
+        rmin = np.min(rspan)
+        rsyyzz = stress["Ryy"][ma] + stress["Rzz"][ma]
+        rsyyzz = rsyyzz / 10.0 ** np.max(np.floor(np.log10(rsyyzz)))
+        # like the reference the abscissa is shifted by rmin while the initial guess and the result are not
+        opt, _ = scipy.optimize.curve_fit(super_gaussian, rspan - rmin, rsyyzz, method="lm",
+                                          p0=(np.max(rsyyzz), rspan[np.argmax(rsyyzz)], np.std(rsyyzz)))
+        return opt[1] * xfact
+
     # ---- AMR -> uniform ----------------------------------------------------------------------------
     def from_amr(self, subdomain_coords=None, refine_level: int = -1, fields=None, filename=None) -> None:
         """Prolong the AMR mesh onto a uniform (sub)domain at `refine_level` (-1 = finest), replace the
