@@ -3,8 +3,7 @@
     per plt file   : reynolds_stress  -> cached in <stem>_analysis_NNNN; flame window from slice_average + fit
     all plt files  : linear fit of the window trajectory
     per plt file   : from_amr of the moving window -> <stem>_uniform_NNNN
-    per uniform    : kinetic_energy_spectra (fractal dimension / structure functions are outside the hot path
-                     and are reported as skipped)
+    per uniform    : fractal_dimension, structure_functions, kinetic_energy_spectra
 
 Settings come from ./pipeline_settings.json (same keys as the reference's fava/pipeline_settings.json); progress
 is checkpointed to ./fava.checkpoint (JSON, next index per stage) and written on SIGINT / SIGTERM as well.
@@ -185,7 +184,8 @@ class Pipeline:
         fn = self.output_dir / self.model.convert_filename_type("uni", "anl").stem
         if dist.is_root():
             print("ANALYSIS: ", fn, flush=True)
-        analyses = {"fractal dimension": None, "structure functions": None,
+        analyses = {"fractal dimension": self.model.fractal_dimension,
+                    "structure functions": self.model.structure_functions,
                     "kinetic energy spectra": self.model.kinetic_energy_spectra}
         keys = list(analyses)
         begin_key = self.checkpoint_data.setdefault(pkey, {}).get("analysis")
@@ -193,10 +193,6 @@ class Pipeline:
         for akey in keys[begin:]:
             self.checkpoint_data[pkey]["analysis"] = akey
             if (self.settings.get(akey) or {}).get("skip", False):
-                continue
-            if analyses[akey] is None:
-                if dist.is_root():
-                    print(f"SKIPPED: {akey} is outside the B200 hot path (DESIGN.md section 8)", flush=True)
                 continue
             retval = analyses[akey](**(self.settings[akey].get("settings", {}) if akey in self.settings else {}))
             dist.barrier()

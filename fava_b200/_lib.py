@@ -14,6 +14,7 @@ _LIB_PATH = Path(__file__).resolve().parent / "lib" / "libfava_b200.so"
 FAVA_F32 = 0
 FAVA_F64 = 1
 FAVA_NMOM = 14
+FAVA_FRACTAL_MAXLEVELS = 32
 
 c_void_p = C.c_void_p
 c_int = C.c_int
@@ -123,6 +124,21 @@ SIGNATURES: dict[str, tuple] = {
     "fava_spectrum_finalize": (
         c_int,
         [c_void_p, c_void_p, c_i64, c_double_p, c_double_p, c_double_p, c_double_p, c_void_p],
+    ),
+    "fava_fractal_tiles": (
+        c_int,
+        [c_void_p, c_void_p, c_int, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_double, c_void_p, c_void_p,
+         c_void_p],
+    ),
+    "fava_fractal_coarse": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_int, c_void_p, c_void_p]),
+    "fava_sf_gather": (
+        c_int,
+        [c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_i64, c_i64, c_i64, c_i64, c_double_p,
+         c_double_p, c_void_p, c_void_p, c_void_p],
+    ),
+    "fava_sf_moments": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_int, c_int, c_void_p, c_void_p],
     ),
     "fava_stage_h2d": (c_int, [c_void_p, C.c_char_p, c_i64, c_i64, c_void_p, c_void_p]),
     "fava_stage_host_h2d": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_void_p]),

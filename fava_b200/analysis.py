@@ -32,3 +32,13 @@ def slice_integral(self, *args, **kwargs):
 @Model.register_analysis(use_timer=True)
 def from_amr(self, *args, **kwargs):
     return self.mesh.from_amr(*args, **kwargs)
+
+
+@Model.register_analysis(use_timer=True)
+def fractal_dimension(self, *args, **kwargs):
+    return self.mesh.fractal_dimension(*args, **kwargs)
+
+
+@Model.register_analysis(use_timer=True)
+def structure_functions(self, *args, **kwargs):
+    return self.mesh.structure_functions(*args, **kwargs)

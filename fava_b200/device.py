@@ -318,6 +318,52 @@ def ke_spectrum(rho, ux, uy, uz) -> dict[str, np.ndarray]:
     return dict(zip(SPECTRUM_KEYS, bufs))
 
 
+# ---- box counting / structure functions (uniform grids) -------------------------------------------------
+def fractal_tiles(field: torch.Tensor, contour: float, nz: int, zf0: int, z0: int, z1: int, counts: torch.Tensor,
+                  coarse: torch.Tensor) -> None:
+    """Flag the contour cells of planes [z0, z1) of a [nz][ny][nx] field (`field` holds planes from zf0 on) and add
+    the filled boxes of levels 0..5 to `counts`, the tile occupancy to `coarse` (fava_fractal_tiles)."""
+    if field.dim() != 3 or not field.is_cuda or not field.is_contiguous():
+        raise ValueError("field must be a contiguous CUDA tensor [z][y][x]")
+    nzl, ny, nx = (int(v) for v in field.shape)
+    ctx = get_context(field.device)
+    _lib.check(ctx.lib.fava_fractal_tiles(ctx.handle, _ptr(field), _dtype_code(field), int(nz), ny, nx, int(zf0),
+                                          int(zf0) + nzl, int(z0), int(z1), float(contour), _ptr(counts), _ptr(coarse),
+                                          _stream(field)), "fava_fractal_tiles")
+
+
+def fractal_coarse(coarse: torch.Tensor, dims_zyx, nlevels: int, counts: torch.Tensor) -> None:
+    """Levels >= 6 from the tile-occupancy grid (fava_fractal_coarse)."""
+    nz, ny, nx = (int(v) for v in dims_zyx)
+    ctx = get_context(coarse.device)
+    _lib.check(ctx.lib.fava_fractal_coarse(ctx.handle, _ptr(coarse), nz, ny, nx, int(nlevels), _ptr(counts),
+                                           _stream(coarse)), "fava_fractal_coarse")
+
+
+def sf_gather(points: torch.Tensor, ux, uy, uz, nz: int, zf0: int, lo, cell, err: torch.Tensor) -> torch.Tensor:
+    """Velocities [npoints][3] of the cells holding `points` [npoints][3]; zeros for planes outside the held slab
+    (fava_sf_gather)."""
+    nzl, ny, nx = _check_fields(ux, ux, uy, uz)
+    ctx = get_context(ux.device)
+    npts = int(points.shape[0])
+    vel = torch.empty((npts, 3), dtype=torch.float64, device=ux.device)
+    h_lo = (C.c_double * 3)(*[float(v) for v in lo])
+    h_cell = (C.c_double * 3)(*[float(v) for v in cell])
+    _lib.check(ctx.lib.fava_sf_gather(ctx.handle, _ptr(points), npts, _ptr(ux), _ptr(uy), _ptr(uz), _dtype_code(ux),
+                                      int(nz), ny, nx, int(zf0), int(zf0) + nzl, h_lo, h_cell, _ptr(vel), _ptr(err),
+                                      _stream(ux)), "fava_sf_gather")
+    return vel
+
+
+def sf_moments(p1, p2, v1, v2, nsep: int, npoints: int, order: int, anisotropic: bool) -> torch.Tensor:
+    """[2][nsep] mean longitudinal / transverse increments to the power `order` (fava_sf_moments)."""
+    ctx = get_context(p1.device)
+    out = torch.empty((2, nsep), dtype=torch.float64, device=p1.device)
+    _lib.check(ctx.lib.fava_sf_moments(ctx.handle, _ptr(p1), _ptr(p2), _ptr(v1), _ptr(v2), int(nsep), int(npoints),
+                                       int(order), int(bool(anisotropic)), _ptr(out), _stream(p1)), "fava_sf_moments")
+    return out
+
+
 # ---- staging ---------------------------------------------------------------------------------------------
 def stage_file(path, file_offset: int, nbytes: int, out: torch.Tensor) -> torch.Tensor:
     """pread `nbytes` at `file_offset` of `path` through the pinned ring into `out` (async on the current stream)."""

@@ -324,6 +324,20 @@ class FLASH(Structured):
         device.stage_file(self._filename, off + b0 * per, (b1 - b0) * per, out)
         return out
 
+    def _stage_plane_range(self, key: str, z0: int, z1: int) -> torch.Tensor:
+        """Planes [z0, z1) of a single-block / 3-D field dataset straight from the file (contiguous byte range)."""
+        if key not in self._extent:
+            raise RuntimeError(f"field {key!r} has no on-disk dataset to stage from")
+        off, nbytes, dtype, shape = self._extent[key]
+        if len(shape) == 4 and shape[0] != 1:
+            raise RuntimeError("plane ranges exist for single-block datasets only")
+        ny, nx = int(shape[-2]), int(shape[-1])
+        per = ny * nx * dtype.itemsize
+        tdt = torch.float32 if dtype.itemsize == 4 else torch.float64
+        out = torch.empty((z1 - z0, ny, nx), dtype=tdt, device=torch.device("cuda", torch.cuda.current_device()))
+        device.stage_file(self._filename, off + z0 * per, (z1 - z0) * per, out)
+        return out
+
     def device_data(self, name: str) -> torch.Tensor:
         """Device tensor of this rank's part of a field, FILE layout ([block][z][y][x] or [z][y][x])."""
         key = self._resolve(name)

@@ -9,7 +9,7 @@ import logging
 
 import numpy as np
 
-from fava_b200 import dist, h5lite, spectrum
+from fava_b200 import dist, h5lite, spectrum, uniform_analysis
 from fava_b200.mesh.flash_mesh import FLASH
 from fava_b200.model import Model
 from fava_b200.util import timer
@@ -69,3 +69,16 @@ class FlashUniform(FLASH):
 
             return device.ke_spectrum(*t)
         return spectrum.slab_ke_spectrum(*t, dims[0])
+
+    @timer
+    def fractal_dimension(self, field: str, contours: list[float] | float = 0.5) -> dict:
+        """Box-counting dimension of the iso-contour of `field` (reference FlashUniform.py:85-227): edge flags and
+        box counts on the GPU, the log-log fit on the host."""
+        return uniform_analysis.fractal_dimension(self, field, contours)
+
+    @timer
+    def structure_functions(self, num_seps: int = 100, num_points: int = 10000, sep_bounds: list[float] = [0.0, 1.0],
+                            log_scale: bool = True, anistropic: bool = False) -> dict:
+        """Longitudinal / transverse velocity structure functions of orders 1..10 (reference FlashUniform.py:306-445);
+        point pairs from np.random like the reference, gathers and reductions on the GPU."""
+        return uniform_analysis.structure_functions(self, num_seps, num_points, sep_bounds, log_scale, anistropic)

@@ -224,6 +224,39 @@ int fava_spectrum_bin(fava_ctx* ctx, const double* d_fx, const double* d_fy, con
 int fava_spectrum_finalize(fava_ctx* ctx, const double* d_sums, int64_t n, double* h_k, double* h_total,
                            double* h_long, double* h_trans, void* stream);
 
+/* ---- uniform-grid analyses next to the spectrum ------------------------------------- */
+
+/* Box counting of an iso-contour (reference: FlashUniform.fractal_dimension, FlashUniform.py:85-227).
+ * d_field holds planes [zf0, zf1) of a [nz][ny][nx] field; the call flags the contour cells of planes [z0, z1)
+ * (edge marking, FlashUniform.py:114-177: the rule int((c - val) / (nb - val)) == 0 decides between the low
+ * cell and its neighbour) and adds to d_counts[level], level = 0..5, the number of boxes of edge 2^level cells
+ * that hold a flag (:179-208); d_coarse [ceil(nz/32)][ceil(ny/32)][ceil(nx/32)] receives the occupancy byte of
+ * every 32^3 tile it visits.  [z0, z1) must be aligned to 32 planes (z1 may be nz) and the buffer must include
+ * one halo plane on each inner side.  The caller zero-fills d_counts (FAVA_FRACTAL_MAXLEVELS entries) and
+ * d_coarse beforehand; several ranks cover disjoint plane ranges and sum both arrays. */
+#define FAVA_FRACTAL_MAXLEVELS 32
+int fava_fractal_tiles(fava_ctx* ctx, const void* d_field, int dtype, int64_t nz, int64_t ny, int64_t nx,
+                       int64_t zf0, int64_t zf1, int64_t z0, int64_t z1, double contour, uint64_t* d_counts,
+                       uint8_t* d_coarse, void* stream);
+/* Levels 6 .. nlevels-1 (box edge 2^(level-5) tiles) from the complete tile-occupancy grid of an [nz][ny][nx]
+ * field, added to d_counts[level]. */
+int fava_fractal_coarse(fava_ctx* ctx, const uint8_t* d_coarse, int64_t nz, int64_t ny, int64_t nx, int nlevels,
+                        uint64_t* d_counts, void* stream);
+
+/* Structure functions (reference: FlashUniform.structure_functions, FlashUniform.py:306-445).
+ * fava_sf_gather: d_points [npoints][3] (x,y,z) -> cell index floor((p - lo) / cell) per axis (:400-406) ->
+ * d_vel [npoints][3] = (velx, vely, velz) of that cell (:408-412) when its plane lies in the held range
+ * [zf0, zf1) of the [nz][ny][nx] fields, 0.0 otherwise (ranks sum their parts).  *d_err is set to 1 if a point
+ * falls outside the grid (the reference raises IndexError there); the caller zeroes it. */
+int fava_sf_gather(fava_ctx* ctx, const double* d_points, int64_t npoints, const void* d_ux, const void* d_uy,
+                   const void* d_uz, int dtype, int64_t nz, int64_t ny, int64_t nx, int64_t zf0, int64_t zf1,
+                   const double* h_lo, const double* h_cell, double* d_vel, int* d_err, void* stream);
+/* fava_sf_moments: for each of nsep separations, over its npoints pairs (p1, p2 coordinates, v1, v2 velocities,
+ * all [nsep][npoints][3]): r^ = (p2 - p1)/|p2 - p1| (or (1,0,0) if anisotropic), dl = |dv . r^|,
+ * dt = |dv - dl r^|; d_out [2][nsep] = mean dl^order, mean dt^order (:417-436). */
+int fava_sf_moments(fava_ctx* ctx, const double* d_p1, const double* d_p2, const double* d_v1, const double* d_v2,
+                    int64_t nsep, int64_t npoints, int order, int anisotropic, double* d_out, void* stream);
+
 /* ---- HDF5 block staging (reference: _read_variable_data, _flash.py:306-341) ----------------- */
 
 /* Stream `nbytes` at `file_offset` of a contiguous HDF5 dataset (offset from the h5lite index)

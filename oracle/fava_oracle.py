@@ -472,3 +472,152 @@ def slice_average(geom: MeshGeom, field: np.ndarray, axis: int = 0):
     layer = (db[others[0], 1] - db[others[0], 0]) * (db[others[1], 1] - db[others[1], 0])
     span, alp = slice_integral(geom, field, axis)
     return span, alp / (geom.min_delta(axis) * layer)
+
+
+# ------------------------------------------------------------------------------------------------
+# §8f rank 4 — FlashUniform.fractal_dimension (fava/mesh/FLASH/FlashUniform.py:85-227)
+# ------------------------------------------------------------------------------------------------
+_NEIGHBOURS = ((1, 0, 0), (0, 1, 0), (0, -1, 0), (-1, 0, 0), (0, 0, 1), (0, 0, -1))  # order of :137-177
+
+
+def fractal_marks_loop(d: np.ndarray, contour: float) -> np.ndarray:
+    """Literal per-cell loop of FlashUniform.py:114-177 (small arrays only): int8[H,W,D] edge flags."""
+    h, w, dp = d.shape
+    e = np.zeros(d.shape, dtype=np.int8)
+    e[d == contour] = 1  # :122
+    for i, j, k in itertools.product(range(1, h - 1), range(1, w - 1), range(1, dp - 1)):  # :133-134
+        val = d[i, j, k]
+        if val < contour:
+            hidx = contour - val
+            for di, dj, dk in _NEIGHBOURS:
+                nb = d[i + di, j + dj, k + dk]
+                if nb > contour:
+                    if int(hidx / (nb - val)) == 0:  # :142, :148, ... crossing nearer to the low cell
+                        e[i, j, k] = 1
+                    else:
+                        e[i + di, j + dj, k + dk] = 1
+    return e
+
+
+def fractal_marks(d: np.ndarray, contour: float) -> np.ndarray:
+    """Vectorised form of the same marking (order-independent: flags are only ever set)."""
+    d = np.asarray(d, dtype=np.float64)
+    h, w, dp = d.shape
+    e = np.zeros(d.shape, dtype=np.int8)
+    e[d == contour] = 1
+    if min(h, w, dp) < 3:
+        return e
+    inner = (slice(1, h - 1), slice(1, w - 1), slice(1, dp - 1))
+    val = d[inner]
+    below = val < contour
+    hidx = contour - val
+    for di, dj, dk in _NEIGHBOURS:
+        shifted = (slice(1 + di, h - 1 + di), slice(1 + dj, w - 1 + dj), slice(1 + dk, dp - 1 + dk))
+        nb = d[shifted]
+        cross = below & (nb > contour)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            near_low = np.trunc(hidx / (nb - val)) == 0  # int(x) == 0
+        e[inner][cross & near_low] = 1
+        e[shifted][cross & ~near_low] = 1
+    return e
+
+
+def box_counts(e: np.ndarray) -> np.ndarray:
+    """Filled boxes per level 0..flength-1, box edge 2^level (FlashUniform.py:179-208)."""
+    h, w, dp = e.shape
+    flength = int(np.log2(min(h, w, dp)) + 1)  # :184 with lowest_level = 0
+    counts = np.zeros(flength, dtype=np.int64)
+    for level in range(flength):
+        b = 2**level
+        if h % b or w % b or dp % b:
+            raise IndexError(f"box edge {b} does not tile a {e.shape} grid (the reference indexes out of bounds here)")
+        boxes = (e.reshape(h // b, b, w // b, b, dp // b, b) > 0).any(axis=(1, 3, 5))
+        counts[level] = int(boxes.sum())
+    return counts
+
+
+def fractal_regression(counts: np.ndarray) -> dict:
+    """FlashUniform.py:207-226 on the integer box counts: keys of one contour's result dict."""
+    counts = np.asarray(counts)
+    flength = counts.shape[0]
+    result = np.zeros((flength, 2))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for level in range(flength):
+            result[level, 0] = flength - level - 1
+            result[level, 1] = np.log2(counts[level])
+        filled_boxes = 2 ** result[:, 1]
+        cum_frac_dim = np.sum(np.log2(filled_boxes[:-1] / filled_boxes[1:]))
+        avg_frac_dim = cum_frac_dim / (filled_boxes.size - 1.0)
+        mean = np.mean(result, axis=0)
+        std = np.std(result, axis=0)
+        rval = np.sum((result[:, 0] - mean[0]) * (result[:, 1] - mean[1])) / (np.prod(std) * result.shape[0])
+        slope = rval * std[1] / std[0]
+        regress = np.array([slope, rval**2, mean[1] - slope * mean[0]])
+    return {"average fractal dimension": avg_frac_dim, "slope": regress[0], "R2": regress[1], "curve": regress[2]}
+
+
+def fractal_dimension(d: np.ndarray, field: str, contour: float) -> dict:
+    """{field: {str(contour): {...}}} for a [i,j,k] float64 array (one float contour, as the reference accepts)."""
+    return {field: {f"{contour}": fractal_regression(box_counts(fractal_marks(d, contour)))}}
+
+
+# ------------------------------------------------------------------------------------------------
+# §8f rank 4 — FlashUniform.structure_functions (FlashUniform.py:306-445)
+# ------------------------------------------------------------------------------------------------
+def structure_function_points(domain_bounds, sep: float, num_points: int):
+    """One separation's random point pairs, consuming numpy's GLOBAL RandomState exactly like
+    FlashUniform.py:361-395: 3*num_points uniforms (point 1), num_points (phi), num_points (theta); point 2 is
+    wrapped periodically into the domain one period at a time."""
+    db = np.asarray(domain_bounds, dtype=np.float64)
+    ndim = db.shape[0]
+    p1 = np.random.random((num_points, ndim)) * np.diff(db, axis=1).ravel() + db[:, 0].ravel()
+    phi = 2.0 * np.pi * np.random.random(num_points)
+    theta = np.arccos(2.0 * np.random.random(num_points) - 1.0)
+    p2 = np.empty_like(p1)
+    p2[:, 0] = p1[:, 0] + sep * np.sin(theta) * np.cos(phi)
+    p2[:, 1] = p1[:, 1] + sep * np.sin(theta) * np.sin(phi)
+    p2[:, 2] = p1[:, 2] + sep * np.cos(theta)
+    for ax in range(3):
+        lo, hi = db[ax]
+        while np.any(p2[:, ax] > hi):
+            p2[p2[:, ax] > hi, ax] += lo - hi
+        while np.any(p2[:, ax] < lo):
+            p2[p2[:, ax] < lo, ax] += hi - lo
+    return p1, p2
+
+
+def structure_functions(vel: dict, ncells_vec, domain_bounds, num_seps=100, num_points=10000, sep_bounds=(0.0, 1.0),
+                        log_scale=True, anistropic=False) -> dict:
+    """vel: {"velx","vely","velz"} float64 [i,j,k].  Orders 1..10, a fresh sample per order (FlashUniform.py:349)."""
+    db = np.asarray(domain_bounds, dtype=np.float64)
+    ncv = np.asarray(ncells_vec)
+    names = ("velx", "vely", "velz")
+    separations = np.geomspace(*sep_bounds, num_seps) if log_scale else np.linspace(*sep_bounds, num_seps)
+    cell_size = np.diff(db, axis=1).flatten() / ncv
+    out = {"transverse": {}, "longitudinal": {}}
+    for order in range(1, 11):
+        pt = np.zeros((num_seps, num_points, 3, 2))
+        dv = np.zeros((num_seps, num_points, 3))
+        for i in range(num_seps):
+            p1, p2 = structure_function_points(db, separations[i], num_points)
+            i1 = [np.floor((p1[:, j] - db[j, 0]) / cell_size[j]).astype(int) for j in range(3)]
+            i2 = [np.floor((p2[:, j] - db[j, 0]) / cell_size[j]).astype(int) for j in range(3)]
+            for j, name in enumerate(names):
+                dv[i, :, j] = vel[name][i2[0], i2[1], i2[2]] - vel[name][i1[0], i1[1], i1[2]]
+            pt[i, ..., 0] = p1
+            pt[i, ..., 1] = p2
+        sep_vec = pt[..., 1] - pt[..., 0]
+        rhat = np.empty_like(sep_vec)
+        if anistropic:
+            rhat[..., 0] = 1.0
+            rhat[..., 1:] = 0.0
+        else:
+            for j in range(3):
+                rhat[..., j] = sep_vec[..., j] / np.sqrt(np.sum(sep_vec**2, axis=2))
+        long_comp = np.abs(np.sum(dv * rhat, axis=2))
+        out["longitudinal"][f"{order}"] = np.sum(long_comp**order, axis=1) / float(num_points)
+        long_dvel = long_comp[..., None] * rhat
+        trans_comp = np.sqrt(np.sum((dv - long_dvel) ** 2, axis=2))
+        out["transverse"][f"{order}"] = np.sum(trans_comp**order, axis=1) / float(num_points)
+        out["separations"] = separations
+    return out

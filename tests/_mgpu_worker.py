@@ -76,6 +76,8 @@ def main():
         fields = synth.block_fields(mesh, names=("dens", "velx", "vely", "velz"), seed=7)
         synth.write_flash_file(tmp / "amr_hdf5_plt_cnt_0000", mesh, fields)
         np.save(tmp / "nblocks.npy", np.array([mesh.nblocks]))
+        synth.write_flash_file(tmp / "uni_hdf5_uniform_0000", synth.single_block_mesh(shape),
+                               {k: full[k].astype(np.float32) for k in full}, uniform3d=True)
     dist.barrier()
     m = fava_b200.mesh.FLASH(tmp / "amr_hdf5_plt_cnt_0000")
     m.load()
@@ -94,8 +96,23 @@ def main():
         s2.load()
         s2.from_amr(np.array([[0.0, 1.0], [0.0, 1.0], [0.0, 1.0]]), fields=["dens"], filename=tmp / f"one{rank}_hdf5_uniform_0000")
         uni_one = s2.data("dens")
+        u1 = fava_b200.mesh.FlashUniform(tmp / "uni_hdf5_uniform_0000")
+        u1.load()
+        fd_one = u1.fractal_dimension("velx", 0.1)
+        np.random.seed(3)
+        sf_one = u1.structure_functions(num_seps=4, num_points=2000, sep_bounds=[0.01, 0.4])
     finally:
         dist.world_size, dist.rank = saved
+    # --- uniform-grid analyses: tile-aligned plane ranges + halo (box counting), slab gathers (structure functions)
+    um = fava_b200.mesh.FlashUniform(tmp / "uni_hdf5_uniform_0000")
+    um.load()
+    fd_many = um.fractal_dimension("velx", 0.1)
+    assert fd_many == fd_one, f"box counting over {world} ranks differs: {fd_many} != {fd_one}"
+    np.random.seed(3)
+    sf_many = um.structure_functions(num_seps=4, num_points=2000, sep_bounds=[0.01, 0.4])
+    for kind in ("longitudinal", "transverse"):
+        for o, v in sf_one[kind].items():
+            assert np.array_equal(sf_many[kind][o], v), f"structure functions {kind} {o} differ over {world} ranks"
     for axis in (0, 1, 2):
         for a, b in zip(res[axis][1].values(), ref[axis][1].values()):
             close(a, b, 1e-13, f"block-range stress axis {axis}")

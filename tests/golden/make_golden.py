@@ -66,10 +66,44 @@ def reynolds_case(name, mesh, fields, tmp, checkpoint=False):
     save(name, **out)
 
 
+def uniform_analysis_cases(tmp):
+    """G6: fractal_dimension and structure_functions of the reference on uniform 3-D files.
+    structure_functions draws from np.random's global state: the seed used is stored with the vectors."""
+    _, RefUniform, _ = rh.ref_modules()
+    for n, dtype in ((16, np.float32), (32, np.float64)):
+        shape = (n, n, n)
+        f = synth.uniform_fields(shape, names=FIELDS, dtype=dtype, seed=4000 + n)
+        pu = tmp / f"g6_{n}_hdf5_uniform_0000"
+        synth.write_flash_file(pu, synth.single_block_mesh(shape, ((0.0, 2.0), (-1.0, 1.0), (0.0, 1.0))), f, uniform3d=True,
+                               checkpoint=dtype is np.float64)
+        m = RefUniform(str(pu))
+        m.load()
+        o = {f"in_{k}": v for k, v in f.items()}
+        o["bounds"] = np.array([[0.0, 2.0], [-1.0, 1.0], [0.0, 1.0]])
+        cases = (("velx", 0.05), ("dens", 1.25), ("vely", float(f["vely"][n // 2, n // 3, n // 4])))
+        o["fd_fields"] = np.array([c[0] for c in cases])
+        o["fd_contours"] = np.array([c[1] for c in cases])
+        for i, (field, contour) in enumerate(cases):
+            res = m.fractal_dimension(field, contour)[field][f"{contour}"]
+            o[f"fd{i}"] = np.array([res[k] for k in ("average fractal dimension", "slope", "R2", "curve")])
+        for tag, kw in (("log", dict(num_seps=5, num_points=300, sep_bounds=[0.02, 0.6], log_scale=True, anistropic=False)),
+                        ("lin_aniso", dict(num_seps=4, num_points=257, sep_bounds=[0.1, 1.3], log_scale=False, anistropic=True))):
+            np.random.seed(977 + n)
+            sf = m.structure_functions(**kw)
+            o[f"sf_{tag}_seed"] = np.array(977 + n)
+            o[f"sf_{tag}_separations"] = np.array(sf["separations"])
+            o[f"sf_{tag}_longitudinal"] = np.stack([sf["longitudinal"][f"{k}"] for k in range(1, 11)])
+            o[f"sf_{tag}_transverse"] = np.stack([sf["transverse"][f"{k}"] for k in range(1, 11)])
+        save(f"g6_uniform_analysis_{n}", **o)
+
+
 def main():
     if not rh.reference_available():
         raise SystemExit("the reference is not mounted; goldens can only be generated in the build container")
     tmp = Path(tempfile.mkdtemp(prefix="fava_golden_"))
+    if "g6" in sys.argv[1:]:  # only the uniform-analysis vectors
+        uniform_analysis_cases(tmp)
+        return
 
     # G1: config 1 in miniature — uniform single-block plt (f32), 32x24x16 cells, non-cubic extent
     shape = (16, 24, 32)
@@ -137,6 +171,8 @@ def main():
         o = {f"in_{k}": v for k, v in f.items()}
         o.update({f"spec_{k}": v for k, v in sp.items()})
         save(f"g5_spectrum_{n}", **o)
+
+    uniform_analysis_cases(tmp)
 
 
 if __name__ == "__main__":

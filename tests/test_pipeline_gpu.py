@@ -34,7 +34,9 @@ def make_run(tmp_path, nfiles=3):
         synth.write_flash_file(tmp_path / f"rt_hdf5_plt_cnt_{i:04d}", mesh, fields, time=0.1 * i)
     settings = {"data folder": str(tmp_path), "output folder": str(tmp_path), "basename": "rt_hdf5_plt_cnt", "dimension": 3,
                 "model": "rt", "reynolds stress": {"skip": False}, "extract windows": {"skip": False},
-                "fractal dimension": {"skip": False}, "structure functions": {"skip": True},
+                "fractal dimension": {"skip": False, "settings": {"field": "flam", "contours": 0.5}},
+                "structure functions": {"skip": False, "settings": {"num_seps": 6, "num_points": 500, "sep_bounds": [1.0 * L, 12.0 * L],
+                                                                     "log_scale": True, "anistropic": False}},
                 "kinetic energy spectra": {"skip": False}}
     (tmp_path / "pipeline_settings.json").write_text(json.dumps(settings))
     return mesh
@@ -47,7 +49,7 @@ def test_pipeline_end_to_end_and_restart(cuda_device, tmp_path, capsys):
     make_run(tmp_path)
     assert main(tmp_path) == 0
     out = capsys.readouterr().out
-    assert "DONE!" in out and "SKIPPED: fractal dimension" in out
+    assert "DONE!" in out
     ck = json.loads((tmp_path / "fava.checkpoint").read_text()) if (tmp_path / "fava.checkpoint").exists() else None
     assert ck is not None and ck["reynolds stress"] == {"index": 3} and ck["extract windows"] == {"index": 3}
     assert ck["analyze uniform data"]["index"] == 3 and ck["analyze uniform data"]["analysis"] is None
@@ -70,6 +72,12 @@ def test_pipeline_end_to_end_and_restart(cuda_device, tmp_path, capsys):
     with h5lite.File(tmp_path / "rt_hdf5_analysis_0001") as f:
         for k in ("k", "total", "longitudinal", "transverse"):
             assert np.array_equal(f["kinetic energy spectra"][k][()], sp[k]), k
+    fd = model.fractal_dimension("flam", 0.5)
+    with h5lite.File(tmp_path / "rt_hdf5_analysis_0001") as f:
+        for k, v in fd["flam"]["0.5"].items():
+            assert np.array_equal(f["fractal dimension"]["flam"]["0.5"][k][()], v, equal_nan=True), k
+        assert f["structure functions"]["longitudinal"]["3"][()].shape == (6,)
+        assert np.all(f["structure functions"]["transverse"]["2"][()] > 0)
     # restart: everything is marked done, nothing is recomputed, cached results are re-used
     before = {p.name: p.stat().st_mtime_ns for p in tmp_path.glob("*uniform*")}
     assert main(tmp_path) == 0
