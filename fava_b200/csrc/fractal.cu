@@ -13,18 +13,29 @@
 // comparison of the two rounded differences — bit-identical decisions (tests/test_uniform_analysis_*.py check the
 // oracle, which divides, against this on adversarial inputs).
 //
-// One CTA owns a 32^3 tile: warps = y rows, lanes = x, marching in z with the z-neighbours carried in registers,
-// x-neighbours by shuffle, y-neighbours through L1.  Every row's flags are one ballot word; the tile's 32x32 words
-// are folded level by level in shared memory (levels 0..5), the tile's occupancy goes to a coarse byte grid from
-// which k_fractal_coarse counts the levels above.  HBM-bound: s bytes per cell read once (+ halo from L1/L2);
-// counts are integers (atomic adds are exact and order-independent).
+// One CTA owns a 32^3 tile and works in four phases on 32-bit row words (one bit per cell of an x row):
+//   A  every row of the tile and of its y/z halo (34 x 34 rows) is read ONCE, coalesced, and classified against the
+//      contour: words lt (val < c), gt (val > c) and, for the tile's own rows, eq (val == c).  f32 data is compared
+//      in f32 against the contour rounded up / down (val < c <=> val < ru(c), val > c <=> val > rd(c): exact);
+//   B  one thread per row combines the words of the six neighbour rows (x neighbours by shifts, the two x-halo
+//      cells of the row loaded by that thread) into CANDIDATES: low visited cells with a high neighbour, high cells
+//      with a low visited neighbour.  Every other cell is decided: flagged iff eq;
+//   C  candidate cells (the cells next to the surface) are evaluated exactly, one lane per cell, with the rule
+//      above on the seven fp64 values (L1/L2 hits: the tile was just read);
+//   D  the 32 x 32 flag words are folded level by level in shared memory (levels 0..5); the tile's occupancy goes
+//      to a coarse byte grid from which k_fractal_coarse counts the levels above.
+// HBM-bound: s bytes per cell read once (+ halo rows from L2); counts are integers (atomic adds are exact and
+// order-independent).
 #include "common.cuh"
 
 namespace fava {
 namespace {
 
 constexpr int kTile = 32;
-constexpr int kTileLevels = 6;  // box edges 1..32 live inside one tile
+constexpr int kHalo = kTile + 2;  // rows per tile edge including the halo
+constexpr int kTileLevels = 6;    // box edges 1..32 live inside one tile
+constexpr int kThreads = 512;
+constexpr int kWarps = kThreads / 32;
 
 // out bit i = in bit 2i | in bit 2i+1
 __device__ __forceinline__ uint32_t fold_pairs(uint32_t m) {
@@ -36,88 +47,199 @@ __device__ __forceinline__ uint32_t fold_pairs(uint32_t m) {
     return m;
 }
 
+// Exact classification of a stored value against the fp64 contour, in the storage precision.
 template <typename T>
-__global__ void __launch_bounds__(1024, 1)
+struct Side;
+template <>
+struct Side<double> {
+    double c;
+    __device__ explicit Side(double contour) : c(contour) {}
+    __device__ __forceinline__ bool lt(double v) const { return v < c; }
+    __device__ __forceinline__ bool gt(double v) const { return v > c; }
+};
+template <>
+struct Side<float> {
+    float up, dn;  // smallest f32 >= c, largest f32 <= c
+    __device__ explicit Side(double contour) {
+#ifdef __CUDA_ARCH__
+        up = __double2float_ru(contour);
+        dn = __double2float_rd(contour);
+#else
+        up = dn = (float)contour;
+#endif
+    }
+    __device__ __forceinline__ bool lt(float v) const { return v < up; }
+    __device__ __forceinline__ bool gt(float v) const { return v > dn; }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 2)
 k_fractal_tiles(const T* __restrict__ f, int64_t nz, int64_t ny, int64_t nx, int64_t zf0, int64_t tz0, double c,
                 unsigned long long* __restrict__ counts, uint8_t* __restrict__ coarse) {
-    __shared__ uint32_t words[2][kTile * kTile];
+    __shared__ uint32_t s_lt[kHalo * kHalo], s_gt[kHalo * kHalo];  // [z + 1][y + 1], halo rows included
+    __shared__ uint32_t s_flag[kTile * kTile], s_cand[kTile * kTile];  // [z][y]
     __shared__ int cnt[kTileLevels];
-    const int lane = threadIdx.x & 31, row = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < kTileLevels) cnt[threadIdx.x] = 0;
 
-    const int64_t x = (int64_t)blockIdx.x * kTile + lane;
-    const int64_t y = (int64_t)blockIdx.y * kTile + row;
+    const int64_t x0 = (int64_t)blockIdx.x * kTile, y0 = (int64_t)blockIdx.y * kTile;
     const int64_t zt = ((int64_t)blockIdx.z + tz0) * kTile;
-    const double nan = __longlong_as_double(0x7ff8000000000000LL);
-    const bool in_xy = x < nx && y < ny;
-    const bool ix = x >= 1 && x <= nx - 2, iy = y >= 1 && y <= ny - 2;
-    const bool ixm = x - 1 >= 1 && x - 1 <= nx - 2, ixp = x + 1 >= 1 && x + 1 <= nx - 2;
-    const bool iym = y - 1 >= 1 && y - 1 <= ny - 2, iyp = y + 1 >= 1 && y + 1 <= ny - 2;
-    const bool has_up = in_xy && y + 1 < ny, has_dn = in_xy && y >= 1;
-    const bool edge_l = lane == 0 && in_xy && x >= 1, edge_r = lane == 31 && in_xy && x + 1 < nx;
-
-    const T* p = f + ((zt - zf0) * ny + (in_xy ? y : 0)) * nx + (in_xy ? x : 0);  // cell (x, y, zt)
     const int64_t plane = ny * nx;
-    auto ld = [&](const T* q, bool ok) -> double { return ok ? (double)__ldg(q) : nan; };
+    const T* base = f - zf0 * plane;  // base[(z * ny + y) * nx + x] for the planes z the buffer holds
+    const Side<T> side(c);
+    const double dnan = __longlong_as_double(0x7ff8000000000000LL);
+    const T tnan = (T)dnan;
 
-    double vm = ld(p - plane, in_xy && zt >= 1);
-    double v0 = ld(p, in_xy && zt < nz);
-#pragma unroll 4
-    for (int s = 0; s < kTile; ++s) {
-        const int64_t z = zt + s;
-        const bool zin = z < nz;
-        const T* q = p + (int64_t)s * plane;
-        const double vp = ld(q + plane, in_xy && z + 1 < nz);
-        const double vu = ld(q + nx, has_up && zin);
-        const double vd = ld(q - nx, has_dn && zin);
-        double vl = __shfl_up_sync(0xffffffffu, v0, 1);
-        double vr = __shfl_down_sync(0xffffffffu, v0, 1);
-        if (lane == 0) vl = ld(q - 1, edge_l && zin);
-        if (lane == 31) vr = ld(q + 1, edge_r && zin);
-
-        const bool iz = z >= 1 && z <= nz - 2;
-        const bool izm = z - 1 >= 1 && z - 1 <= nz - 2, izp = z + 1 >= 1 && z + 1 <= nz - 2;
-        bool m = v0 == c;
-        if (v0 < c) {
-            if (ix && iy && iz) {  // this cell is visited by the reference loop: near crossings flag it
-                const double h = c - v0;
-                m = m || (vr > c && h < vr - v0) || (vl > c && h < vl - v0) || (vu > c && h < vu - v0) ||
-                    (vd > c && h < vd - v0) || (vp > c && h < vp - v0) || (vm > c && h < vm - v0);
-            }
-        } else if (v0 > c) {  // a visited low neighbour n flags this cell when its crossing is not near n
-            m = m || (ixm && iy && iz && vl < c && !(c - vl < v0 - vl)) ||
-                (ixp && iy && iz && vr < c && !(c - vr < v0 - vr)) ||
-                (ix && iym && iz && vd < c && !(c - vd < v0 - vd)) ||
-                (ix && iyp && iz && vu < c && !(c - vu < v0 - vu)) ||
-                (ix && iy && izm && vm < c && !(c - vm < v0 - vm)) ||
-                (ix && iy && izp && vp < c && !(c - vp < v0 - vp));
+    // ---- A: classify the rows of the tile and of its y/z halo (the four corner lines are never needed) ---------
+    // Loads are issued in register batches before any vote so that kBatch row requests per warp are in flight.
+    const bool x_in = x0 + lane < nx;
+    auto classify = [&](T v, int zzi, int yyi) {  // halo-inclusive row coordinates 0..33
+        const bool lt = side.lt(v), gt = side.gt(v);
+        const uint32_t wl = __ballot_sync(0xffffffffu, lt), wg = __ballot_sync(0xffffffffu, gt);
+        uint32_t we = 0;
+        if ((wl | wg) != 0xffffffffu) we = __ballot_sync(0xffffffffu, !lt && !gt && v == v);  // warp-uniform
+        if (lane == 0) {
+            s_lt[zzi * kHalo + yyi] = wl;
+            s_gt[zzi * kHalo + yyi] = wg;
+            if (zzi >= 1 && zzi <= kTile && yyi >= 1 && yyi <= kTile) s_flag[(zzi - 1) * kTile + (yyi - 1)] = we;
         }
-        const uint32_t w = __ballot_sync(0xffffffffu, m);
-        if (lane == 0) words[0][s * kTile + row] = w;
-        vm = v0;
-        v0 = vp;
+    };
+    constexpr int kBatch = sizeof(T) == 4 ? 12 : 9;
+#pragma unroll 1
+    for (int yyi = warp + 1; yyi <= kTile; yyi += kWarps) {  // z-march over the tile's own y rows
+        const int64_t y = y0 + yyi - 1;
+        const bool ok = x_in && y < ny;
+        const T* p = base + ((zt - 1) * ny + y) * nx + x0 + lane;  // row (y, zt - 1); dereferenced only when valid
+#pragma unroll 1
+        for (int zb = 0; zb < kHalo; zb += kBatch) {
+            T v[kBatch];
+#pragma unroll
+            for (int b = 0; b < kBatch; ++b) {
+                const int64_t z = zt - 1 + zb + b;
+                v[b] = (ok && zb + b < kHalo && z >= 0 && z < nz) ? __ldg(p + (int64_t)(zb + b) * plane) : tnan;
+            }
+#pragma unroll
+            for (int b = 0; b < kBatch; ++b)
+                if (zb + b < kHalo) classify(v[b], zb + b, yyi);
+        }
+    }
+    {  // the two y-halo lines of the tile: 2 x 32 rows, four per warp
+        T v[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int zzi = 1 + 2 * warp + (b & 1), yyi = (b >> 1) * (kTile + 1);
+            const int64_t z = zt + zzi - 1, y = y0 + yyi - 1;
+            v[b] = (x_in && z < nz && y >= 0 && y < ny) ? __ldg(base + (z * ny + y) * nx + x0 + lane) : tnan;
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) classify(v[b], 1 + 2 * warp + (b & 1), (b >> 1) * (kTile + 1));
     }
     __syncthreads();
 
-    // level 0: flagged cells; levels 1..5: fold 2x2x2 children (x pairs inside the word, y/z pairs across words)
+    // ---- B: candidates, one thread per row -------------------------------------------------------------------
+    uint32_t xvis = 0;  // bit i: cell x0 + i is visited by the reference loop along x (1 <= x <= nx - 2)
+    {
+        const int64_t lo = max((int64_t)1, x0), hi = min(nx - 2, x0 + kTile - 1);
+        if (hi >= lo) xvis = (uint32_t)((((uint64_t)1 << (hi - lo + 1)) - 1) << (lo - x0));
+    }
+    const bool xvis_left = x0 - 1 >= 1 && x0 - 1 <= nx - 2, xvis_right = x0 + kTile <= nx - 2;
+    for (int row = threadIdx.x; row < kTile * kTile; row += kThreads) {
+        const int zz = row / kTile, yy = row % kTile;
+        const int64_t z = zt + zz, y = y0 + yy;
+        uint32_t cand = 0;
+        if (z < nz && y < ny) {
+            const int h = (zz + 1) * kHalo + (yy + 1);
+            const uint32_t l = s_lt[h], g = s_gt[h];
+            const T* rowp = base + (z * ny + y) * nx + x0;
+            const T vl = x0 >= 1 ? __ldg(rowp - 1) : tnan;  // the row's two x-halo cells
+            const T vr = x0 + kTile < nx ? __ldg(rowp + kTile) : tnan;
+            const bool yv = y >= 1 && y <= ny - 2, zv = z >= 1 && z <= nz - 2;
+            const bool yv_m = y - 1 >= 1, yv_p = y + 1 <= ny - 2, zv_m = z - 1 >= 1, zv_p = z + 1 <= nz - 2;
+            if (yv && zv) {
+                // low visited cells with a high neighbour
+                const uint32_t g_any = (g >> 1) | (side.gt(vr) ? 0x80000000u : 0u) | (g << 1) | (side.gt(vl) ? 1u : 0u) |
+                                       s_gt[h + 1] | s_gt[h - 1] | s_gt[h + kHalo] | s_gt[h - kHalo];
+                cand = l & xvis & g_any;
+            }
+            // high cells with a low visited neighbour
+            uint32_t l_vis = 0;
+            if (yv && zv) {
+                const uint32_t lx = l & xvis;
+                l_vis = (lx >> 1) | ((xvis_right && side.lt(vr)) ? 0x80000000u : 0u) | (lx << 1) |
+                        ((xvis_left && side.lt(vl)) ? 1u : 0u);
+            }
+            if (yv_p && zv) l_vis |= s_lt[h + 1] & xvis;
+            if (yv_m && zv) l_vis |= s_lt[h - 1] & xvis;
+            if (yv && zv_p) l_vis |= s_lt[h + kHalo] & xvis;
+            if (yv && zv_m) l_vis |= s_lt[h - kHalo] & xvis;
+            cand |= g & l_vis;
+        }
+        s_cand[row] = cand;
+    }
+    __syncthreads();
+
+    // ---- C: exact rule on the candidate cells, one lane per cell ----------------------------------------------
+    {
+        const int64_t x = x0 + lane;
+        const bool xv = x >= 1 && x <= nx - 2, xv_m = x - 1 >= 1 && x - 1 <= nx - 2, xv_p = x + 1 >= 1 && x + 1 <= nx - 2;
+        for (int row = warp; row < kTile * kTile; row += kWarps) {
+            const uint32_t cand = s_cand[row];
+            if (cand == 0) continue;  // warp-uniform
+            bool m = false;
+            if ((cand >> lane) & 1u) {
+                const int64_t z = zt + row / kTile, y = y0 + row % kTile;
+                const T* q = base + (z * ny + y) * nx + x;
+                const double v0 = (double)__ldg(q);
+                const double vl = x >= 1 ? (double)__ldg(q - 1) : dnan, vr = x + 1 < nx ? (double)__ldg(q + 1) : dnan;
+                const double vd = y >= 1 ? (double)__ldg(q - nx) : dnan, vu = y + 1 < ny ? (double)__ldg(q + nx) : dnan;
+                const double vm = z >= 1 ? (double)__ldg(q - plane) : dnan, vp = z + 1 < nz ? (double)__ldg(q + plane) : dnan;
+                const bool yv = y >= 1 && y <= ny - 2, zv = z >= 1 && z <= nz - 2;
+                const bool yv_m = y - 1 >= 1 && y - 1 <= ny - 2, yv_p = y + 1 >= 1 && y + 1 <= ny - 2;
+                const bool zv_m = z - 1 >= 1 && z - 1 <= nz - 2, zv_p = z + 1 >= 1 && z + 1 <= nz - 2;
+                if (v0 < c) {
+                    if (xv && yv && zv) {  // visited by the reference loop: near crossings flag this cell
+                        const double h = c - v0;
+                        m = (vr > c && h < vr - v0) || (vl > c && h < vl - v0) || (vu > c && h < vu - v0) ||
+                            (vd > c && h < vd - v0) || (vp > c && h < vp - v0) || (vm > c && h < vm - v0);
+                    }
+                } else if (v0 > c) {  // a visited low neighbour n flags this cell when its crossing is not near n
+                    m = (xv_m && yv && zv && vl < c && !(c - vl < v0 - vl)) ||
+                        (xv_p && yv && zv && vr < c && !(c - vr < v0 - vr)) ||
+                        (xv && yv_m && zv && vd < c && !(c - vd < v0 - vd)) ||
+                        (xv && yv_p && zv && vu < c && !(c - vu < v0 - vu)) ||
+                        (xv && yv && zv_m && vm < c && !(c - vm < v0 - vm)) ||
+                        (xv && yv && zv_p && vp < c && !(c - vp < v0 - vp));
+                }
+            }
+            const uint32_t w = __ballot_sync(0xffffffffu, m);
+            if (lane == 0 && w) s_flag[row] |= w;
+        }
+    }
+    __syncthreads();
+
+    // ---- D: level 0 = flagged cells; levels 1..5 fold 2x2x2 children (x pairs inside the word, y/z across words)
+    uint32_t* src = s_flag;
+    uint32_t* dst = s_cand;
     int edge = kTile;
-    int src = 0;
     for (int level = 0; level < kTileLevels; ++level) {
-        uint32_t w = 0;
+        int n = 0;
         if (level == 0) {
-            w = words[0][threadIdx.x];
+            for (int i = threadIdx.x; i < kTile * kTile; i += kThreads) n += __popc(src[i]);
         } else {
             const int half = edge >> 1;
-            if ((int)threadIdx.x < half * half) {
-                const int zz = threadIdx.x / half, yy = threadIdx.x % half;
-                const uint32_t* a = &words[src][(2 * zz) * edge + 2 * yy];
-                w = fold_pairs(a[0] | a[1] | a[edge] | a[edge + 1]);
-                words[src ^ 1][zz * half + yy] = w;
+            for (int i = threadIdx.x; i < half * half; i += kThreads) {
+                const int zz = i / half, yy = i % half;
+                const uint32_t* a = &src[(2 * zz) * edge + 2 * yy];
+                const uint32_t w = fold_pairs(a[0] | a[1] | a[edge] | a[edge + 1]);
+                dst[i] = w;
+                n += __popc(w);
             }
             edge = half;
-            src ^= 1;
+            uint32_t* t = src;
+            src = dst;
+            dst = t;
         }
-        const int n = __reduce_add_sync(0xffffffffu, __popc(w));
+        n = __reduce_add_sync(0xffffffffu, n);
         if (lane == 0 && n) atomicAdd(&cnt[level], n);
         __syncthreads();
     }

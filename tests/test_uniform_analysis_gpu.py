@@ -96,7 +96,7 @@ def test_box_counts_adversarial_ties_and_exact_hits(cuda_device):
 
 
 def test_box_counts_split_over_plane_ranges_equal_one_call(cuda_device):
-    f = synth.uniform_fields((128, 64, 96), names=("velx",), dtype=np.float32, seed=5)["velx"]
+    f = synth.uniform_fields((128, 64, 192), names=("velx",), dtype=np.float32, seed=5)["velx"]
     whole = box_counts_gpu(f, 0.1)
     assert np.array_equal(whole, box_counts_gpu(f, 0.1, splits=[(0, 32), (32, 96), (96, 128)]))
     assert np.array_equal(whole, oracle_counts(f, 0.1))
