@@ -300,10 +300,10 @@ int fava_fractal_tiles(fava_ctx* ctx, const void* d_field, int dtype, int64_t nz
     dim3 grid((unsigned)ctx_, (unsigned)cty, (unsigned)(tz1 - tz0));
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == FAVA_F64)
-        k_fractal_tiles<double><<<grid, 1024, 0, st>>>((const double*)d_field, nz, ny, nx, zf0, tz0, contour,
+        k_fractal_tiles<double><<<grid, kThreads, 0, st>>>((const double*)d_field, nz, ny, nx, zf0, tz0, contour,
                                                        (unsigned long long*)d_counts, d_coarse);
     else
-        k_fractal_tiles<float><<<grid, 1024, 0, st>>>((const float*)d_field, nz, ny, nx, zf0, tz0, contour,
+        k_fractal_tiles<float><<<grid, kThreads, 0, st>>>((const float*)d_field, nz, ny, nx, zf0, tz0, contour,
                                                       (unsigned long long*)d_counts, d_coarse);
     FAVA_LAUNCHED();
     return FAVA_OK;
