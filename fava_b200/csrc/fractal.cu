@@ -78,9 +78,11 @@ k_fractal_tiles(const T* __restrict__ f, int64_t nz, int64_t ny, int64_t nx, int
                 unsigned long long* __restrict__ counts, uint8_t* __restrict__ coarse) {
     __shared__ uint32_t s_lt[kHalo * kHalo], s_gt[kHalo * kHalo];  // [z + 1][y + 1], halo rows included
     __shared__ uint32_t s_flag[kTile * kTile], s_cand[kTile * kTile];  // [z][y]
-    __shared__ int cnt[kTileLevels];
+    __shared__ uint16_t s_rows[kTile * kTile];  // rows holding candidates (any order)
+    __shared__ int cnt[kTileLevels], s_nrows;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < kTileLevels) cnt[threadIdx.x] = 0;
+    if (threadIdx.x == kTileLevels) s_nrows = 0;
 
     const int64_t x0 = (int64_t)blockIdx.x * kTile, y0 = (int64_t)blockIdx.y * kTile;
     const int64_t zt = ((int64_t)blockIdx.z + tz0) * kTile;
@@ -175,6 +177,7 @@ k_fractal_tiles(const T* __restrict__ f, int64_t nz, int64_t ny, int64_t nx, int
             cand |= g & l_vis;
         }
         s_cand[row] = cand;
+        if (cand) s_rows[atomicAdd(&s_nrows, 1)] = (uint16_t)row;
     }
     __syncthreads();
 
@@ -182,9 +185,10 @@ k_fractal_tiles(const T* __restrict__ f, int64_t nz, int64_t ny, int64_t nx, int
     {
         const int64_t x = x0 + lane;
         const bool xv = x >= 1 && x <= nx - 2, xv_m = x - 1 >= 1 && x - 1 <= nx - 2, xv_p = x + 1 >= 1 && x + 1 <= nx - 2;
-        for (int row = warp; row < kTile * kTile; row += kWarps) {
+        const int nrows = s_nrows;
+        for (int i = warp; i < nrows; i += kWarps) {
+            const int row = s_rows[i];
             const uint32_t cand = s_cand[row];
-            if (cand == 0) continue;  // warp-uniform
             bool m = false;
             if ((cand >> lane) & 1u) {
                 const int64_t z = zt + row / kTile, y = y0 + row % kTile;
@@ -249,27 +253,36 @@ k_fractal_tiles(const T* __restrict__ f, int64_t nz, int64_t ny, int64_t nx, int
         coarse[(((int64_t)blockIdx.z + tz0) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = (uint8_t)(cnt[5] != 0);
 }
 
-// Levels >= 6 on the tile-occupancy grid [ctz][cty][ctx]: box edge 2^(level-5) tiles.
-__global__ void k_fractal_coarse(const uint8_t* __restrict__ coarse, int64_t ctz, int64_t cty, int64_t ctx_, int nlevels,
-                                 unsigned long long* __restrict__ counts) {
+// Levels >= 6: repeated 2x2x2 OR-reduction of the tile-occupancy grid [sz][sy][sx] (one CTA; the reduced grids
+// ping-pong between two workspace buffers), counting the occupied boxes of every level.
+__global__ void __launch_bounds__(1024)
+k_fractal_coarse(const uint8_t* __restrict__ coarse, int64_t sz, int64_t sy, int64_t sx, int nlevels, uint8_t* w0,
+                 uint8_t* w1, unsigned long long* __restrict__ counts) {
+    __shared__ unsigned long long total;
+    const uint8_t* src = coarse;
+    uint8_t* dst = w0;
     for (int level = kTileLevels; level < nlevels; ++level) {
-        const int64_t e = (int64_t)1 << (level - (kTileLevels - 1));
-        const int64_t bx = (ctx_ + e - 1) / e, by = (cty + e - 1) / e, bz = (ctz + e - 1) / e;
+        const int64_t dz = (sz + 1) / 2, dy = (sy + 1) / 2, dx = (sx + 1) / 2;
+        if (threadIdx.x == 0) total = 0;
+        __syncthreads();
         unsigned long long mine = 0;
-        for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < bx * by * bz;
-             b += (int64_t)gridDim.x * blockDim.x) {
-            const int64_t x0 = (b % bx) * e, y0 = ((b / bx) % by) * e, z0 = (b / (bx * by)) * e;
-            bool filled = false;
-            for (int64_t z = z0; z < min(z0 + e, ctz) && !filled; ++z)
-                for (int64_t y = y0; y < min(y0 + e, cty) && !filled; ++y)
-                    for (int64_t x = x0; x < min(x0 + e, ctx_); ++x)
-                        if (coarse[(z * cty + y) * ctx_ + x]) {
-                            filled = true;
-                            break;
-                        }
-            mine += filled;
+        for (int64_t i = threadIdx.x; i < dz * dy * dx; i += blockDim.x) {
+            const int64_t x = 2 * (i % dx), y = 2 * ((i / dx) % dy), z = 2 * (i / (dx * dy));
+            unsigned o = 0;
+            for (int64_t zz = z; zz < min(z + 2, sz); ++zz)
+                for (int64_t yy = y; yy < min(y + 2, sy); ++yy)
+                    for (int64_t xx = x; xx < min(x + 2, sx); ++xx) o |= src[(zz * sy + yy) * sx + xx];
+            dst[i] = (uint8_t)(o != 0);
+            mine += o != 0;
         }
-        if (mine) atomicAdd(&counts[level], mine);
+        if (mine) atomicAdd(&total, mine);
+        __syncthreads();  // the block's writes to dst are visible to the block after the barrier
+        if (threadIdx.x == 0 && total) atomicAdd(&counts[level], total);
+        src = dst;
+        dst = dst == w0 ? w1 : w0;
+        sz = dz;
+        sy = dy;
+        sx = dx;
     }
 }
 
@@ -318,8 +331,12 @@ int fava_fractal_coarse(fava_ctx* ctx, const uint8_t* d_coarse, int64_t nz, int6
     if (nlevels <= kTileLevels) return FAVA_OK;
     DeviceGuard g(ctx->device);
     const int64_t ctx_ = (nx + kTile - 1) / kTile, cty = (ny + kTile - 1) / kTile, ctz = (nz + kTile - 1) / kTile;
-    k_fractal_coarse<<<32, 256, 0, (cudaStream_t)stream>>>(d_coarse, ctz, cty, ctx_, nlevels,
-                                                           (unsigned long long*)d_counts);
+    const int64_t half = ((ctz + 1) / 2) * ((cty + 1) / 2) * ((ctx_ + 1) / 2);
+    void* ws = nullptr;
+    int rc = ctx_workspace(ctx, WS_AUX, (size_t)(2 * half), &ws);
+    if (rc != FAVA_OK) return rc;
+    k_fractal_coarse<<<1, 1024, 0, (cudaStream_t)stream>>>(d_coarse, ctz, cty, ctx_, nlevels, (uint8_t*)ws,
+                                                           (uint8_t*)ws + half, (unsigned long long*)d_counts);
     FAVA_LAUNCHED();
     return FAVA_OK;
 }

@@ -32,7 +32,12 @@ def main():
         f = torch.rand((n, n, n), generator=g, device=dev, dtype=dt)
         counts = torch.zeros(32, dtype=torch.int64, device=dev)
         coarse = torch.zeros([(n + 31) // 32] * 3, dtype=torch.uint8, device=dev)
-        for contour, tag in ((0.5, "noise"), (2.0, "empty")):
+        ar = torch.arange(n, device=dev, dtype=torch.float64)
+        sheet = (ar[None, None, :] - 0.5 * n - 0.25 - 20.0 * torch.sin(2 * np.pi * ar / n)[None, :, None]
+                 * torch.cos(4 * np.pi * ar / n)[:, None, None]).to(dt)  # a wrinkled surface: the realistic case
+        for contour, tag in ((0.5, "noise"), (2.0, "empty"), (0.0, "sheet")):
+            if tag == "sheet":
+                f = sheet
             def run():
                 counts.zero_()
                 device.fractal_tiles(f, contour, n, 0, 0, n, counts, coarse)
@@ -44,7 +49,7 @@ def main():
                 "ms": ms, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / ms / 1e6,
                 "frac_of_hbm_peak": nbytes / ms / 1e6 / peak, "gcells_per_s": n**3 / ms / 1e6,
                 "note": "counts.zero_ + fava_fractal_tiles" + ("" if tiles_only else " + fava_fractal_coarse")}
-        del f
+        del f, sheet
     n = 512
     vel = [torch.rand((n, n, n), generator=g, device=dev, dtype=torch.float32) for _ in range(3)]
     nsep, npts = 100, 10000
