@@ -26,6 +26,9 @@
 //      to a coarse byte grid from which k_fractal_coarse counts the levels above.
 // HBM-bound: s bytes per cell read once (+ halo rows from L2); counts are integers (atomic adds are exact and
 // order-independent).
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace fava {
@@ -34,8 +37,6 @@ namespace {
 constexpr int kTile = 32;
 constexpr int kHalo = kTile + 2;  // rows per tile edge including the halo
 constexpr int kTileLevels = 6;    // box edges 1..32 live inside one tile
-constexpr int kThreads = 512;
-constexpr int kWarps = kThreads / 32;
 
 // out bit i = in bit 2i | in bit 2i+1
 __device__ __forceinline__ uint32_t fold_pairs(uint32_t m) {
@@ -72,14 +73,15 @@ struct Side<float> {
     __device__ __forceinline__ bool gt(float v) const { return v > dn; }
 };
 
-template <typename T>
-__global__ void __launch_bounds__(kThreads, 2)
+template <typename T, int kThreads, int kMinCtas>
+__global__ void __launch_bounds__(kThreads, kMinCtas)
 k_fractal_tiles(const T* __restrict__ f, int64_t nz, int64_t ny, int64_t nx, int64_t zf0, int64_t tz0, double c,
                 unsigned long long* __restrict__ counts, uint8_t* __restrict__ coarse) {
     __shared__ uint32_t s_lt[kHalo * kHalo], s_gt[kHalo * kHalo];  // [z + 1][y + 1], halo rows included
     __shared__ uint32_t s_flag[kTile * kTile], s_cand[kTile * kTile];  // [z][y]
     __shared__ uint16_t s_rows[kTile * kTile];  // rows holding candidates (any order)
     __shared__ int cnt[kTileLevels], s_nrows;
+    constexpr int kWarps = kThreads / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < kTileLevels) cnt[threadIdx.x] = 0;
     if (threadIdx.x == kTileLevels) s_nrows = 0;
@@ -125,16 +127,17 @@ k_fractal_tiles(const T* __restrict__ f, int64_t nz, int64_t ny, int64_t nx, int
                 if (zb + b < kHalo) classify(v[b], zb + b, yyi);
         }
     }
-    {  // the two y-halo lines of the tile: 2 x 32 rows, four per warp
-        T v[4];
+    {  // the two y-halo lines of the tile: 2 x 32 rows, kYh per warp
+        constexpr int kYh = 2 * kTile / kWarps, kPer = kYh / 2;
+        T v[kYh];
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int zzi = 1 + 2 * warp + (b & 1), yyi = (b >> 1) * (kTile + 1);
+        for (int b = 0; b < kYh; ++b) {
+            const int zzi = 1 + kPer * warp + (b % kPer), yyi = (b / kPer) * (kTile + 1);
             const int64_t z = zt + zzi - 1, y = y0 + yyi - 1;
             v[b] = (x_in && z < nz && y >= 0 && y < ny) ? __ldg(base + (z * ny + y) * nx + x0 + lane) : tnan;
         }
 #pragma unroll
-        for (int b = 0; b < 4; ++b) classify(v[b], 1 + 2 * warp + (b & 1), (b >> 1) * (kTile + 1));
+        for (int b = 0; b < kYh; ++b) classify(v[b], 1 + kPer * warp + (b % kPer), (b / kPer) * (kTile + 1));
     }
     __syncthreads();
 
@@ -312,12 +315,27 @@ int fava_fractal_tiles(fava_ctx* ctx, const void* d_field, int dtype, int64_t nz
     FAVA_REQUIRE(cty <= 65535 && tz1 - tz0 <= 65535, "fava_fractal_tiles: grid too large");
     dim3 grid((unsigned)ctx_, (unsigned)cty, (unsigned)(tz1 - tz0));
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == FAVA_F64)
-        k_fractal_tiles<double><<<grid, kThreads, 0, st>>>((const double*)d_field, nz, ny, nx, zf0, tz0, contour,
-                                                       (unsigned long long*)d_counts, d_coarse);
-    else
-        k_fractal_tiles<float><<<grid, kThreads, 0, st>>>((const float*)d_field, nz, ny, nx, zf0, tz0, contour,
-                                                      (unsigned long long*)d_counts, d_coarse);
+    // CTA shape: 256 threads x up to 6 CTAs per SM overlaps the phases of different tiles best (measured on B200);
+    // FAVA_FRACTAL_CTA = 512x2 | 512x3 | 256x4 | 256x6 selects another one for tuning.
+    const char* shape = getenv("FAVA_FRACTAL_CTA");
+    const int which = !shape ? 3 : !strcmp(shape, "512x2") ? 0 : !strcmp(shape, "512x3") ? 1 : !strcmp(shape, "256x4") ? 2 : 3;
+#define FAVA_FRACTAL_LAUNCH(T, TH, MC)                                                                       \
+    k_fractal_tiles<T, TH, MC><<<grid, TH, 0, st>>>((const T*)d_field, nz, ny, nx, zf0, tz0, contour,          \
+                                                    (unsigned long long*)d_counts, d_coarse)
+#define FAVA_FRACTAL_DISPATCH(T)                                \
+    switch (which) {                                            \
+        case 0: FAVA_FRACTAL_LAUNCH(T, 512, 2); break;          \
+        case 1: FAVA_FRACTAL_LAUNCH(T, 512, 3); break;          \
+        case 2: FAVA_FRACTAL_LAUNCH(T, 256, 4); break;          \
+        default: FAVA_FRACTAL_LAUNCH(T, 256, 6); break;         \
+    }
+    if (dtype == FAVA_F64) {
+        FAVA_FRACTAL_DISPATCH(double)
+    } else {
+        FAVA_FRACTAL_DISPATCH(float)
+    }
+#undef FAVA_FRACTAL_DISPATCH
+#undef FAVA_FRACTAL_LAUNCH
     FAVA_LAUNCHED();
     return FAVA_OK;
 }
