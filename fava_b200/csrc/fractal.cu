@@ -315,10 +315,11 @@ int fava_fractal_tiles(fava_ctx* ctx, const void* d_field, int dtype, int64_t nz
     FAVA_REQUIRE(cty <= 65535 && tz1 - tz0 <= 65535, "fava_fractal_tiles: grid too large");
     dim3 grid((unsigned)ctx_, (unsigned)cty, (unsigned)(tz1 - tz0));
     cudaStream_t st = (cudaStream_t)stream;
-    // CTA shape: 256 threads x up to 6 CTAs per SM overlaps the phases of different tiles best (measured on B200);
-    // FAVA_FRACTAL_CTA = 512x2 | 512x3 | 256x4 | 256x6 selects another one for tuning.
+    // CTA shape: the kernel is bound by its per-row instruction stream, not by occupancy — 512x2, 512x3, 256x4 and
+    // 256x6 (threads x CTAs/SM) measure within 15 % of each other on B200 (profiles/r01_uniform_analysis_kernels.json);
+    // 256x4 is the default, FAVA_FRACTAL_CTA selects another one for tuning.
     const char* shape = getenv("FAVA_FRACTAL_CTA");
-    const int which = !shape ? 3 : !strcmp(shape, "512x2") ? 0 : !strcmp(shape, "512x3") ? 1 : !strcmp(shape, "256x4") ? 2 : 3;
+    const int which = !shape ? 2 : !strcmp(shape, "512x2") ? 0 : !strcmp(shape, "512x3") ? 1 : !strcmp(shape, "256x6") ? 3 : 2;
 #define FAVA_FRACTAL_LAUNCH(T, TH, MC)                                                                       \
     k_fractal_tiles<T, TH, MC><<<grid, TH, 0, st>>>((const T*)d_field, nz, ny, nx, zf0, tz0, contour,          \
                                                     (unsigned long long*)d_counts, d_coarse)
