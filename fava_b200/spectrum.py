@@ -129,7 +129,33 @@ def exchange(p: SlabPlan, c: int) -> None:
         device.a2a_pack(p.send[c], p.peer_tables[c], p.ky_of_dest, p.rank, p.world, p.nzl, p.n, p.nyl)
 
 
-def slab_ke_spectrum(rho, ux, uy, uz, n: int, overlap=None, epilogue=None) -> dict[str, np.ndarray]:
+def spectral_buffers(n: int, nz_local: int, dev) -> list[int]:
+    """Device addresses of the three per-component buffers the weighting + 2-D transform of a z-slab fill (real
+    [nz_local][n][2(n/2+1)] -> complex [nz_local][n][n/2+1] in place): the slab plan's send buffers on several
+    ranks, the workspaces of fava_ke_spectrum on one."""
+    world = dist.world_size()
+    if world == 1:
+        return [device.workspace(4 + c, 16 * n * n * (n // 2 + 1), dev) for c in range(3)]  # WS_FFT1 + c
+    return _plan(n, dist.rank(), world, dev).send
+
+
+def spectrum_from_transformed_slabs(n: int, dev, epilogue=None) -> dict[str, np.ndarray]:
+    """Rest of the spectrum once `spectral_buffers` hold the 2-D transforms of this rank's planes (filled chunk
+    by chunk while the slab was still arriving from the host, stats.host_step): exchange, z transforms, binning."""
+    if dist.world_size() > 1:
+        return slab_ke_spectrum(None, None, None, None, n, epilogue=epilogue, xy_done=True, dev=dev)
+    w = spectral_buffers(n, n, dev)
+    sums = torch.zeros((3, n // 2 - 1), dtype=torch.float64, device=dev)
+    for c in range(3):
+        device.fft_z(w[c], n, n * (n // 2 + 1), dev)
+    device.spectrum_bin(w[0], w[1], w[2], n, n, None, None, sums)
+    if epilogue is not None:
+        epilogue()
+    return device.spectrum_finalize(sums, n)
+
+
+def slab_ke_spectrum(rho, ux, uy, uz, n: int, overlap=None, epilogue=None, xy_done: bool = False,
+                     dev=None) -> dict[str, np.ndarray]:
     """Spectrum of the global N^3 grid formed by the ranks' z-slabs; every rank returns the full dict.
 
     Schedule: the exchange of component c (K5, NVLink-bound, on a side stream) overlaps the 2-D transforms
@@ -144,15 +170,18 @@ def slab_ke_spectrum(rho, ux, uy, uz, n: int, overlap=None, epilogue=None) -> di
             if hook is not None:
                 hook()
         return device.ke_spectrum(rho, ux, uy, uz)
-    nzl = int(rho.shape[0])
-    if nzl * world != n or tuple(rho.shape[1:]) != (n, n):
-        raise ValueError(f"rank {rank}: slab shape {tuple(rho.shape)} is not [{n // world}][{n}][{n}]")
-    p = _plan(n, rank, world, rho.device)
-    dev = rho.device
+    if not xy_done:
+        nzl = int(rho.shape[0])
+        if nzl * world != n or tuple(rho.shape[1:]) != (n, n):
+            raise ValueError(f"rank {rank}: slab shape {tuple(rho.shape)} is not [{n // world}][{n}][{n}]")
+        dev = rho.device
+    p = _plan(n, rank, world, dev)
     cur = torch.cuda.current_stream(dev)
-    device.ke_weight3(rho, ux, uy, uz, *p.send)
+    if not xy_done:
+        device.ke_weight3(rho, ux, uy, uz, *p.send)
     for c in range(3):
-        device.fft_xy(p.send[c], p.nzl, n, n, dev)
+        if not xy_done:  # else the send buffers already hold the 2-D transforms (spectrum_from_transformed_slabs)
+            device.fft_xy(p.send[c], p.nzl, n, n, dev)
         p.ev_xy[c].record(cur)
         with torch.cuda.stream(p.comm_stream):
             p.comm_stream.wait_event(p.ev_xy[c])

@@ -127,3 +127,73 @@ def slab_step(rho, ux, uy, uz, n: int, cell_volume: float, layer_volume: float, 
         local_moments()
         finish_profiles()
     return out
+
+
+def host_step(host, n: int, cell_volume: float, layer_volume: float, axes=(0, 1, 2), spectrum: bool = True,
+              favre: bool = True, chunk_planes: int = 64, stage=None) -> dict:
+    """`slab_step` for a snapshot that still lives in HOST memory (pinned tensors rho, ux, uy, uz of this rank's
+    z-slab [nz_local][n][n]): the slab is copied to HBM in chunks of `chunk_planes` planes on a side stream and
+    every chunk is consumed as soon as it has landed — plane moments accumulated about the pivots of the first
+    chunk, weighting + 2-D transforms written into the spectral buffers — so that all the HBM-bound work except
+    the z transforms and the binning hides behind the PCIe copy.  Same result dict as `slab_step`."""
+    from fava_b200 import spectrum as spec
+
+    nzl = int(host[0].shape[0])
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if stage is None:
+        stage = [torch.empty(h.shape, dtype=h.dtype, device=dev) for h in host]
+    cur = torch.cuda.current_stream(dev)
+    copy_stream = _copy_stream(dev)
+    copy_stream.wait_stream(cur)  # earlier users of `stage` on the calling stream
+    chunks = [(a, min(a + chunk_planes, nzl)) for a in range(0, nzl, chunk_planes)]
+    landed = []
+    with torch.cuda.stream(copy_stream):
+        for a, b in chunks:
+            for h, s in zip(host, stage):
+                s[a:b].copy_(h[a:b], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+            landed.append(ev)
+
+    w = spec.spectral_buffers(n, nzl, dev) if spectrum else None
+    plane_bytes = 16 * n * (n // 2 + 1)  # one z-plane of a spectral buffer: complex [n][n/2+1]
+    mom, piv = {}, {}
+    for (a, b), ev in zip(chunks, landed):
+        cur.wait_event(ev)
+        part = [s[a:b] for s in stage]
+        for ax in axes:
+            if ax in (0, 1):  # the planes cross every chunk: accumulate about the first chunk's pivots
+                if a == 0:
+                    mom[ax], piv[ax] = device.plane_moments(*part, ax)
+                else:
+                    device.plane_moments(*part, ax, pivots=piv[ax], out=mom[ax], accumulate=True)
+            else:  # z planes are chunk-local
+                m, pv = device.plane_moments(*part, ax)
+                if a == 0:
+                    mom[ax] = torch.empty((m.shape[0], nzl), dtype=m.dtype, device=dev)
+                    piv[ax] = torch.empty((pv.shape[0], nzl), dtype=pv.dtype, device=dev)
+                mom[ax][:, a:b] = m
+                piv[ax][:, a:b] = pv
+        if spectrum:
+            device.ke_weight_fft_xy(*part, *[p + a * plane_bytes for p in w])
+    out = {}
+
+    def finish_profiles():
+        for ax in axes:
+            out[ax] = slab_profiles_finish(mom[ax], piv[ax], ax, cell_volume, layer_volume, favre=favre, gather=False)
+
+    if spectrum:
+        out["spectrum"] = spec.spectrum_from_transformed_slabs(n, dev, epilogue=finish_profiles)
+    else:
+        finish_profiles()
+    return out
+
+
+_copy_streams: dict = {}
+
+
+def _copy_stream(dev) -> torch.cuda.Stream:
+    key = str(dev)
+    if key not in _copy_streams:
+        _copy_streams[key] = torch.cuda.Stream(device=dev)
+    return _copy_streams[key]

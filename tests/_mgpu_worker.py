@@ -67,6 +67,14 @@ def main():
         ref_ax = device.plane_profiles(*tf, axis, cv, lv)
         for k in ref_ax:
             close(step[axis][k].cpu().numpy(), ref_ax[k].cpu().numpy(), 1e-13, f"slab_step profiles {k} axis {axis}")
+    # the same step streamed from pinned host memory in chunks (stats.host_step)
+    host = [t.cpu().pin_memory() for t in ts]
+    hs = stats.host_step(host, n, cv, lv, chunk_planes=max(1, (z1 - z0) // 3))
+    for k in one:
+        close(hs["spectrum"][k], one[k], 1e-13, f"host_step spectrum {k}")
+    for axis in (0, 1, 2):
+        for k in step[axis]:
+            close(hs[axis][k].cpu().numpy(), step[axis][k].cpu().numpy(), 1e-13, f"host_step profiles {k} axis {axis}")
 
     # --- block datasets: contiguous block ranges per rank, file -> staging -> kernels
     tmp = Path(tempfile.gettempdir()) / f"fava_mgpu_{os.environ.get('MASTER_PORT', '0')}"
