@@ -116,3 +116,44 @@ def test_result_writer_matches_reference_writer(tmp_path):
     same(trees[0], trees[1])
     assert np.array_equal(trees[1]["reynolds stresses"]["tensor"]["Rxy"], np.zeros(4))
     assert float(trees[1]["scalars"]["time"]) == 0.25
+
+
+@pytest.mark.parametrize("shape,field,contour,seed", [((16, 32, 64), "velx", 0.1, 51), ((8, 8, 8), "dens", 1.3, 52),
+                                                      ((32, 16, 16), "vely", -0.2, 53)])
+def test_fractal_dimension_reference_equals_oracle(tmp_path, shape, field, contour, seed):
+    """§8f rank 4 on non-cubic grids and other seeds than the goldens (shape is [z][y][x])."""
+    f = synth.uniform_fields(shape, names=FIELDS, dtype=np.float32, seed=seed)
+    p = tmp_path / "fd_hdf5_uniform_0000"
+    synth.write_flash_file(p, synth.single_block_mesh(shape), f, uniform3d=True)
+    _, RefUniform, _ = rh.ref_modules()
+    m = RefUniform(str(p))
+    m.load()
+    ref = m.fractal_dimension(field, contour)
+    got = orc.fractal_dimension(orc.load_like_reference(f[field]), field, contour)
+    assert list(ref) == list(got) and list(ref[field]) == list(got[field])
+    for k, v in ref[field][f"{contour}"].items():
+        assert np.array_equal(v, got[field][f"{contour}"][k], equal_nan=True), k
+    with pytest.raises(ValueError):
+        m.fractal_dimension(field, [contour])  # the reference accepts a single float only (FlashUniform.py:87-90)
+
+
+def test_structure_functions_reference_equals_oracle_with_wrapping(tmp_path):
+    """Separations longer than the domain (several periodic wraps) on a non-cubic box."""
+    shape = (8, 16, 32)
+    bounds = ((-1.0, 3.0), (0.0, 0.5), (2.0, 3.0))
+    f = synth.uniform_fields(shape, names=FIELDS, dtype=np.float32, seed=61)
+    p = tmp_path / "sf_hdf5_uniform_0000"
+    synth.write_flash_file(p, synth.single_block_mesh(shape, bounds), f, uniform3d=True)
+    _, RefUniform, _ = rh.ref_modules()
+    m = RefUniform(str(p))
+    m.load()
+    kw = dict(num_seps=3, num_points=400, sep_bounds=[0.3, 2.2], log_scale=False)
+    np.random.seed(5)
+    ref = m.structure_functions(**kw)
+    np.random.seed(5)
+    got = orc.structure_functions({k: orc.load_like_reference(f[k]) for k in FIELDS[1:]}, (32, 16, 8), bounds, **kw)
+    for kind in ("longitudinal", "transverse"):
+        for o in ref[kind]:
+            assert np.array_equal(ref[kind][o], got[kind][o]), (kind, o)
+    with pytest.raises(ValueError):
+        m.structure_functions()  # default sep_bounds [0, 1] with log_scale: np.geomspace refuses 0
