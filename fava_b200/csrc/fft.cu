@@ -19,6 +19,7 @@
 // in-place DIF is digit-reversed, which costs nothing here: rows are written back to their true frequency
 // (column passes) or gathered by frequency (x pass, with a skewed layout against bank conflicts).
 // Twiddles come from one exp(-2 pi i m / N) table per N, computed on the host in long double.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <vector>
@@ -271,6 +272,79 @@ __global__ void __launch_bounds__(kFftThreads, 2)
     }
 }
 
+// Persistent form of the fused x pass: one CTA per SM walks row pairs; the eight input rows of the NEXT pair
+// (rho, ux, uy, uz x 2 rows = four contiguous 2N-element spans) are fetched by bulk copies (TMA, cp.async.bulk +
+// mbarrier) into a raw staging buffer while the current pair is transformed and written, so the global loads
+// overlap the shared-memory phases inside the CTA instead of relying on a second resident CTA.
+template <typename T, int LOGN>
+__global__ void __launch_bounds__(512, 1)
+    k_fft_x_weight_tma(const T* __restrict__ rho, const T* __restrict__ ux, const T* __restrict__ uy,
+                       const T* __restrict__ uz, int64_t nrows, const double2* __restrict__ tw, double2* __restrict__ fx,
+                       double2* __restrict__ fy, double2* __restrict__ fz) {
+    constexpr int N = 1 << LOGN, NH = N / 2 + 1;
+    constexpr int PITCH = skew(N - 1) + 2;
+    extern __shared__ __align__(16) unsigned char fft_smem[];
+    double2* sm = reinterpret_cast<double2*>(fft_smem);                           // [3][PITCH]
+    T* raw = reinterpret_cast<T*>(fft_smem + sizeof(double2) * 3 * PITCH);        // [4 fields][2 rows][N]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(fft_smem + sizeof(double2) * 3 * PITCH + sizeof(T) * 8 * N);
+    const int nthreads = blockDim.x;
+    const int64_t npairs = (nrows + 1) / 2;
+    const T* src[4] = {rho, ux, uy, uz};
+
+    auto issue = [&](int64_t pair) {  // thread 0 only
+        const int64_t r0 = 2 * pair;
+        const unsigned bytes = (unsigned)(min((int64_t)2, nrows - r0) * N * sizeof(T));
+        mbar_expect_tx(bar, 4 * bytes);
+#pragma unroll
+        for (int f = 0; f < 4; ++f) bulk_load(raw + f * 2 * N, src[f] + r0 * N, bytes, bar);
+    };
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async;\n" ::: "memory");
+        if ((int64_t)blockIdx.x < npairs) issue(blockIdx.x);
+    }
+    __syncthreads();
+
+    unsigned parity = 0;
+    double2* out[3] = {fx, fy, fz};
+    for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+        const int64_t r0 = 2 * pair;
+        const bool two = r0 + 1 < nrows;
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+        // z_c[n] = w_c[r0][n] + i w_c[r0+1][n],  w = sqrt(rho) u, from the staged rows
+        for (int n = threadIdx.x; n < N; n += nthreads) {
+            const double ra = (double)raw[n];
+            const double rb = two ? (double)raw[N + n] : 0.0;
+            const double sa = sqrt(ra), sb = sqrt(rb);
+            const int p = skew(n);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const double a = (double)raw[(c + 1) * 2 * N + n];
+                const double b = two ? (double)raw[(c + 1) * 2 * N + N + n] : 0.0;
+                sm[c * PITCH + p] = make_double2(sa * a, sb * b);
+            }
+        }
+        __syncthreads();  // the staged rows are consumed: refill them for the next pair while this one is transformed
+        if (threadIdx.x == 0 && pair + gridDim.x < npairs) issue(pair + gridDim.x);
+        fft_lines_smem<LOGN, false>(sm, 3, PITCH, tw);
+        for (int k = threadIdx.x; k < NH; k += nthreads) {
+            const int ia = skew(freq_to_pos<LOGN>(k)), ib = skew(freq_to_pos<LOGN>((N - k) & (N - 1)));
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const double2 A = sm[c * PITCH + ia], B = sm[c * PITCH + ib];
+                const double2 e = make_double2(0.5 * (A.x + B.x), 0.5 * (A.y - B.y));
+                const double2 o = make_double2(0.5 * (A.y + B.y), 0.5 * (B.x - A.x));
+                __stcs(&out[c][r0 * NH + k], e);
+                if (two) __stcs(&out[c][(r0 + 1) * NH + k], o);
+            }
+        }
+        __syncthreads();  // the transform buffer is free again
+    }
+}
+
 // ---- strided column pass ------------------------------------------------------------------------------------
 // data: complex [nbatch][N][ncols]; transform along the middle axis for every (batch, column).
 template <int LOGN, int C, int THREADS>
@@ -346,15 +420,17 @@ static int ilog2_pow2(int64_t v) {
     return l;
 }
 
-bool fft_native_supported(int64_t n) {
-    // Opt-in (FAVA_FFT=native) in this round: measured at 1024^3 on B200 the fused x pass takes 20.2 ms against
-    // 21.9 ms for K4 + cuFFT's x pass, but the strided passes (7.6 / 6.4 ms with 8-column tiles) are still
-    // slower than cuFFT's 5.4 ms: their shared-memory phases do not yet overlap the loads (profiles/).
+// FAVA_FFT selects the spectrum's transform engine: "cufft" (default) = K4 + cuFFT; "native" = every pass
+// hand-written (fused x pass, strided y pass, disc-pruned z pass); "hybrid" = the fused, TMA-prefetching x pass + one
+// cuFFT rank-2 (z, y) strided plan per component.  Measured numbers: DESIGN.md section 4 / profiles/.
+int fft_mode(int64_t n) {
     const int l = ilog2_pow2(n);
     const char* e = getenv("FAVA_FFT");
-    if (!e || e[0] != 'n') return false;
-    return l >= 6 && l <= 12;
+    if (!e || l < 6 || l > 12) return 0;
+    return e[0] == 'n' ? 1 : (e[0] == 'h' ? 2 : 0);
 }
+
+bool fft_native_supported(int64_t n) { return fft_mode(n) == 1; }
 
 template <typename T, int LOGN>
 static int launch_x(const T* rho, const T* ux, const T* uy, const T* uz, int64_t nrows, const double2* tw, double2* fx,
@@ -364,6 +440,30 @@ static int launch_x(const T* rho, const T* ux, const T* uy, const T* uz, int64_t
     FAVA_CHECK_CUDA(cudaFuncSetAttribute(k_fft_x_weight<T, LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_fft_x_weight<T, LOGN><<<(unsigned)((nrows + 1) / 2), kFftThreads, smem, st>>>(rho, ux, uy, uz, nrows, tw, fx, fy, fz);
     FAVA_LAUNCHED();
+    return FAVA_OK;
+}
+
+// Persistent TMA-prefetching x pass when its buffers (transform lines + staged rows) fit one CTA's shared memory
+// (N <= 1024 for f64 input, N <= 2048 for f32); FAVA_FFT_X=plain keeps the two-CTA kernel, FAVA_FFT_X_THREADS sets
+// the CTA size (default 512).
+template <typename T, int LOGN>
+static int launch_x_tma(fava_ctx* ctx, const T* rho, const T* ux, const T* uy, const T* uz, int64_t nrows,
+                        const double2* tw, double2* fx, double2* fy, double2* fz, cudaStream_t st, bool* done) {
+    constexpr int N = 1 << LOGN;
+    const size_t smem = sizeof(double2) * 3 * (skew(N - 1) + 2) + sizeof(T) * 8 * N + 16;
+    *done = false;
+    const char* e = getenv("FAVA_FFT_X");
+    if (smem > 227 * 1024 || (e && e[0] == 'p')) return FAVA_OK;
+    int threads = 512;
+    if (const char* t = getenv("FAVA_FFT_X_THREADS")) threads = atoi(t) == 256 ? 256 : (atoi(t) == 384 ? 384 : 512);
+    FAVA_CHECK_CUDA(cudaFuncSetAttribute(k_fft_x_weight_tma<T, LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    FAVA_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fft_x_weight_tma<T, LOGN>, threads, smem));
+    const int64_t npairs = (nrows + 1) / 2;
+    const unsigned grid = (unsigned)std::min<int64_t>(npairs, (int64_t)ctx->num_sms * std::max(per_sm, 1));
+    k_fft_x_weight_tma<T, LOGN><<<grid, threads, smem, st>>>(rho, ux, uy, uz, nrows, tw, fx, fy, fz);
+    FAVA_LAUNCHED();
+    *done = true;
     return FAVA_OK;
 }
 
@@ -411,10 +511,19 @@ static int launch_cols(double2* data, int64_t ncols, int64_t nbatch, const doubl
         default: return set_error(FAVA_EINVAL, "native FFT: N = 2^%d is not supported", l);    \
     }
 
+template <typename T, int LOGN>
+static int launch_x_any(fava_ctx* ctx, const T* rho, const T* ux, const T* uy, const T* uz, int64_t nrows,
+                        const double2* tw, double2* fx, double2* fy, double2* fz, cudaStream_t st) {
+    bool done = false;
+    const int rc = launch_x_tma<T, LOGN>(ctx, rho, ux, uy, uz, nrows, tw, fx, fy, fz, st, &done);
+    if (rc || done) return rc;
+    return launch_x<T, LOGN>(rho, ux, uy, uz, nrows, tw, fx, fy, fz, st);
+}
+
 template <typename T>
-static int dispatch_x(int l, const T* rho, const T* ux, const T* uy, const T* uz, int64_t nrows, const double2* tw,
-                      double2* fx, double2* fy, double2* fz, cudaStream_t st) {
-#define CALL_X(L) launch_x<T, L>(rho, ux, uy, uz, nrows, tw, fx, fy, fz, st)
+static int dispatch_x(fava_ctx* ctx, int l, const T* rho, const T* ux, const T* uy, const T* uz, int64_t nrows,
+                      const double2* tw, double2* fx, double2* fy, double2* fz, cudaStream_t st) {
+#define CALL_X(L) launch_x_any<T, L>(ctx, rho, ux, uy, uz, nrows, tw, fx, fy, fz, st)
     FAVA_LOGN_SWITCH(l, CALL_X)
 #undef CALL_X
 }
@@ -447,9 +556,9 @@ int fava_fft_x_weight3(fava_ctx* ctx, const void* d_rho, const void* d_ux, const
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == FAVA_F64)
-        return dispatch_x<double>(l, (const double*)d_rho, (const double*)d_ux, (const double*)d_uy, (const double*)d_uz,
+        return dispatch_x<double>(ctx, l, (const double*)d_rho, (const double*)d_ux, (const double*)d_uy, (const double*)d_uz,
                                   nrows, tw, (double2*)d_fx, (double2*)d_fy, (double2*)d_fz, st);
-    return dispatch_x<float>(l, (const float*)d_rho, (const float*)d_ux, (const float*)d_uy, (const float*)d_uz, nrows, tw,
+    return dispatch_x<float>(ctx, l, (const float*)d_rho, (const float*)d_ux, (const float*)d_uy, (const float*)d_uz, nrows, tw,
                              (double2*)d_fx, (double2*)d_fy, (double2*)d_fz, st);
 }
 

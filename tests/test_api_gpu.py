@@ -280,27 +280,53 @@ def test_data_returns_reference_layout(fava, tmp_path):
     assert m.data("no such field") is None
 
 
+@pytest.mark.parametrize("mode", ["native", "hybrid"])
 @pytest.mark.parametrize("n,dtype", [(64, np.float32), (256, np.float64), (512, np.float32)])
-def test_native_fft_path_matches_cufft_path(cuda_device, monkeypatch, n, dtype):
+def test_native_fft_path_matches_cufft_path(cuda_device, monkeypatch, n, dtype, mode):
     """FAVA_FFT=native routes power-of-two grids through the hand-written line FFTs (x pass fused with the
-    weighting, strided y pass, disc-pruned z pass) instead of cuFFT.  Same spectra to 1e-13."""
+    weighting and fed by TMA bulk copies, strided y pass, disc-pruned z pass) instead of cuFFT; FAVA_FFT=hybrid keeps
+    the fused x pass and hands the (z, y) passes to one cuFFT plan.  Same spectra to 1e-13."""
     import torch
 
     from fava_b200 import _lib, device
 
-    monkeypatch.setenv("FAVA_FFT", "native")
-    assert _lib.load().fava_fft_native_supported(n) == 1 and _lib.load().fava_fft_native_supported(96) == 0
+    monkeypatch.setenv("FAVA_FFT", mode)
+    assert _lib.load().fava_fft_native_supported(n) == (1 if mode == "native" else 0)
+    assert _lib.load().fava_fft_native_supported(96) == 0
     g = torch.Generator(device=cuda_device)
     g.manual_seed(n)
     tdt = torch.float64 if dtype == np.float64 else torch.float32
     rho = (1.0 + 0.5 * torch.rand((n, n, n), generator=g, device=cuda_device, dtype=torch.float64)).to(tdt)
     u = [(torch.randn((n, n, n), generator=g, device=cuda_device, dtype=torch.float64) + 0.3 * i).to(tdt) for i in range(3)]
     native = device.ke_spectrum(rho, *u)
+    monkeypatch.setenv("FAVA_FFT_X", "plain")  # the two-CTA x kernel without the TMA prefetch
+    plain = device.ke_spectrum(rho, *u)
+    monkeypatch.delenv("FAVA_FFT_X")
     monkeypatch.delenv("FAVA_FFT")
     assert _lib.load().fava_fft_native_supported(n) == 0
     library = device.ke_spectrum(rho, *u)
     for k in ("k", "total", "longitudinal", "transverse"):
         maxnorm_close(native[k], library[k], 1e-13, f"{k} n={n}")
+        assert np.array_equal(native[k], plain[k]), f"{k}: TMA-fed and plain x pass differ"
+
+
+def test_fft_x_pass_odd_row_count_and_small_grids(cuda_device):
+    """The persistent x pass on a row count that is odd and smaller than the grid of CTAs."""
+    import torch
+
+    from fava_b200 import device
+
+    n = 128
+    for nrows in (1, 7, 300):
+        g = torch.Generator(device=cuda_device)
+        g.manual_seed(nrows)
+        f = [torch.rand((1, nrows, n), generator=g, device=cuda_device, dtype=torch.float64) + 0.5 for _ in range(4)]
+        out = [torch.zeros((nrows, n // 2 + 1), dtype=torch.complex128, device=cuda_device) for _ in range(3)]
+        device.fft_x_weight3(*f, *[o.data_ptr() for o in out])
+        for c in range(3):
+            ref = torch.fft.rfft(torch.sqrt(f[0][0]) * f[c + 1][0], dim=-1)
+            err = (out[c] - ref).abs().max().item() / ref.abs().max().item()
+            assert err <= 1e-13, (nrows, c, err)
 
 
 def test_staging_file_and_host_paths_are_byte_exact(cuda_device, tmp_path):
