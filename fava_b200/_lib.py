@@ -109,7 +109,6 @@ SIGNATURES: dict[str, tuple] = {
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_i64, c_void_p, c_void_p, c_void_p, c_void_p],
     ),
     "fava_fft_z": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_void_p]),
-    "fava_fft_zy": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_void_p]),
     "fava_a2a_pack": (
         c_int,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_i64, c_i64, c_i64, c_void_p],

@@ -79,8 +79,6 @@ int ctx_workspace(fava_ctx* ctx, int slot, size_t bytes, void** out);
 
 // native (hand-written) FFT available for this grid size?  (power of two in [64, 4096], not FAVA_FFT=cufft)
 bool fft_native_supported(int64_t n);
-// 0 = cuFFT, 1 = native, 2 = hybrid (native x pass + cuFFT (z, y) plan); see csrc/fft.cu
-int fft_mode(int64_t n);
 
 struct DeviceGuard {
     int prev = -1;

@@ -420,17 +420,17 @@ static int ilog2_pow2(int64_t v) {
     return l;
 }
 
-// FAVA_FFT selects the spectrum's transform engine: "cufft" (default) = K4 + cuFFT; "native" = every pass
-// hand-written (fused x pass, strided y pass, disc-pruned z pass); "hybrid" = the fused, TMA-prefetching x pass + one
-// cuFFT rank-2 (z, y) strided plan per component.  Measured numbers: DESIGN.md section 4 / profiles/.
-int fft_mode(int64_t n) {
+bool fft_native_supported(int64_t n) {
+    // Opt-in (FAVA_FFT=native).  Measured at 1024^3 fp64 on B200 (tools/fft_bench.py, profiles/r01_fft_native.txt): the
+    // fused x pass takes 16.9 ms with the TMA-fed persistent kernel (21.0 ms for the two-CTA kernel) against 21.9 ms
+    // for K4 + cuFFT's x pass, but the strided passes (9.0 / 7.3 ms per component) are slower than cuFFT's 5.4 ms, and
+    // cuFFT offers no efficient plan for the remaining (z, y) passes on their own (a rank-2 strided plan over the two
+    // slow axes takes 59 ms per component), so the x pass cannot be combined with cuFFT's column passes either.
     const int l = ilog2_pow2(n);
     const char* e = getenv("FAVA_FFT");
-    if (!e || l < 6 || l > 12) return 0;
-    return e[0] == 'n' ? 1 : (e[0] == 'h' ? 2 : 0);
+    if (!e || e[0] != 'n') return false;
+    return l >= 6 && l <= 12;
 }
-
-bool fft_native_supported(int64_t n) { return fft_mode(n) == 1; }
 
 template <typename T, int LOGN>
 static int launch_x(const T* rho, const T* ux, const T* uy, const T* uz, int64_t nrows, const double2* tw, double2* fx,
@@ -445,7 +445,7 @@ static int launch_x(const T* rho, const T* ux, const T* uy, const T* uz, int64_t
 
 // Persistent TMA-prefetching x pass when its buffers (transform lines + staged rows) fit one CTA's shared memory
 // (N <= 1024 for f64 input, N <= 2048 for f32); FAVA_FFT_X=plain keeps the two-CTA kernel, FAVA_FFT_X_THREADS sets
-// the CTA size (default 512).
+// the CTA size (default 384).
 template <typename T, int LOGN>
 static int launch_x_tma(fava_ctx* ctx, const T* rho, const T* ux, const T* uy, const T* uz, int64_t nrows,
                         const double2* tw, double2* fx, double2* fy, double2* fz, cudaStream_t st, bool* done) {
@@ -454,8 +454,8 @@ static int launch_x_tma(fava_ctx* ctx, const T* rho, const T* ux, const T* uy, c
     *done = false;
     const char* e = getenv("FAVA_FFT_X");
     if (smem > 227 * 1024 || (e && e[0] == 'p')) return FAVA_OK;
-    int threads = 512;
-    if (const char* t = getenv("FAVA_FFT_X_THREADS")) threads = atoi(t) == 256 ? 256 : (atoi(t) == 384 ? 384 : 512);
+    int threads = 384;  // measured: 256 / 384 / 512 threads -> 17.7 / 16.9 / 17.3 ms
+    if (const char* t = getenv("FAVA_FFT_X_THREADS")) threads = atoi(t) == 256 ? 256 : (atoi(t) == 512 ? 512 : 384);
     FAVA_CHECK_CUDA(cudaFuncSetAttribute(k_fft_x_weight_tma<T, LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     FAVA_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fft_x_weight_tma<T, LOGN>, threads, smem));

@@ -291,7 +291,7 @@ __global__ void k_spectrum_reduce(const double* __restrict__ partial, int ncta, 
 // ------------------------------------------------------------------------------------------------
 // cuFFT plans (cached in the context; one shared work area)
 // ------------------------------------------------------------------------------------------------
-enum PlanKind { PLAN_XY = 1, PLAN_Z = 2, PLAN_ZY = 3 };
+enum PlanKind { PLAN_XY = 1, PLAN_Z = 2 };
 
 static int get_plan(fava_ctx* ctx, int kind, int64_t a, int64_t b, int64_t c, cufftHandle* out) {
     const auto key = std::make_tuple(kind, a, b, c);
@@ -312,10 +312,6 @@ static int get_plan(fava_ctx* ctx, int kind, int64_t a, int64_t b, int64_t c, cu
         long long onembed[2] = {(long long)b, nxh};
         r = cufftMakePlanMany64(h, 2, dims, inembed, 1, (long long)b * 2 * nxh, onembed, 1, (long long)b * nxh,
                                 CUFFT_D2Z, (long long)a, &work);
-    } else if (kind == PLAN_ZY) {  // a = n (z and y length), b = columns (stride and batch): in-place 2-D Z2Z over
-                                   // the two slow axes of complex [a][a][b]
-        long long dims[2] = {(long long)a, (long long)a};
-        r = cufftMakePlanMany64(h, 2, dims, dims, (long long)b, 1, dims, (long long)b, 1, CUFFT_Z2Z, (long long)b, &work);
     } else {  // a = nz (transform length), b = rows (stride and batch) : in-place strided 1-D Z2Z
         long long dims[1] = {(long long)a};
         long long embed[1] = {(long long)a};
@@ -389,13 +385,6 @@ int fava_fft_xy(fava_ctx* ctx, double* d_data, int64_t nz_local, int64_t ny, int
     FAVA_REQUIRE(nz_local > 0 && ny > 0 && nx > 1 && (nx & 1) == 0, "fava_fft_xy: bad shape");
     DeviceGuard g(ctx->device);
     return exec_plan(ctx, PLAN_XY, nz_local, ny, nx, d_data, (cudaStream_t)stream);
-}
-
-int fava_fft_zy(fava_ctx* ctx, double* d_data, int64_t n, int64_t ncols, void* stream) {
-    FAVA_REQUIRE(ctx && d_data, "fava_fft_zy: NULL argument");
-    FAVA_REQUIRE(n > 0 && ncols > 0, "fava_fft_zy: bad shape");
-    DeviceGuard g(ctx->device);
-    return exec_plan(ctx, PLAN_ZY, n, ncols, 0, d_data, (cudaStream_t)stream);
 }
 
 int fava_fft_z(fava_ctx* ctx, double* d_data, int64_t nz, int64_t rows, void* stream) {
@@ -527,16 +516,7 @@ int fava_ke_spectrum(fava_ctx* ctx, const void* d_rho, const void* d_ux, const v
     void* sums;
     rc = ctx_workspace(ctx, WS_AUX, sizeof(double) * 3 * (size_t)(n / 2 - 1), &sums);
     if (rc) return rc;
-    if (fft_mode(n) == 2) {
-        // hybrid: fused weighting + x pass (csrc/fft.cu), then one cuFFT plan over (z, y) per component
-        rc = fava_fft_x_weight3(ctx, d_rho, d_ux, d_uy, d_uz, dtype, n * n, n, (double*)w[0], (double*)w[1],
-                                (double*)w[2], stream);
-        if (rc) return rc;
-        for (int c = 0; c < 3; ++c) {
-            rc = fava_fft_zy(ctx, (double*)w[c], n, nxh, stream);
-            if (rc) return rc;
-        }
-    } else if (fft_native_supported(n)) {
+    if (fft_native_supported(n)) {
         // hand-written path: weighting fused into the x pass, strided y pass, disc-pruned z pass (csrc/fft.cu)
         rc = fava_fft_x_weight3(ctx, d_rho, d_ux, d_uy, d_uz, dtype, n * n, n, (double*)w[0], (double*)w[1],
                                 (double*)w[2], stream);

@@ -446,12 +446,6 @@ def fft_z(data: int, nz: int, rows: int, dev) -> None:
     _lib.check(ctx.lib.fava_fft_z(ctx.handle, C.c_void_p(data), nz, rows, _cur_stream(dev)), "fava_fft_z")
 
 
-def fft_zy(data: int, n: int, ncols: int, dev) -> None:
-    """In-place 2-D FFT over the two slow axes of complex [n][n][ncols] (fava_fft_zy, one cuFFT plan)."""
-    ctx = get_context(dev)
-    _lib.check(ctx.lib.fava_fft_zy(ctx.handle, C.c_void_p(data), n, ncols, _cur_stream(dev)), "fava_fft_zy")
-
-
 def a2a_pack(src: int, peer_table: torch.Tensor, ky_of_dest: torch.Tensor, rank: int, world: int, nz_local: int, n: int,
              nyl: int) -> None:
     ctx = get_context(peer_table.device)

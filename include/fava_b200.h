@@ -196,9 +196,6 @@ int fava_fft_xy(fava_ctx* ctx, double* d_data, int64_t nz_local, int64_t ny, int
 int fava_ke_weight_fft_xy(fava_ctx* ctx, const void* d_rho, const void* d_ux, const void* d_uy, const void* d_uz,
                           int dtype, int64_t nz_local, int64_t n, double* d_wx, double* d_wy, double* d_wz,
                           void* stream);
-/* In-place 2-D c2c FFT (one cuFFT Z2Z plan) over the two slow axes of complex [n][n][ncols] (the y and z passes
- * after fava_fft_x_weight3: ncols = nx/2+1). */
-int fava_fft_zy(fava_ctx* ctx, double* d_data, int64_t n, int64_t ncols, void* stream);
 /* In-place c2c FFTs (cuFFT Z2Z) along the slowest axis of complex [nz][rows] (rows = ny_local*(nx/2+1)). */
 int fava_fft_z(fava_ctx* ctx, double* d_data, int64_t nz, int64_t rows, void* stream);
 /* Slab -> ky-pencil exchange, fused with the pack: rank `my_rank` holds complex [nz_local][n][nxh] after

@@ -280,19 +280,16 @@ def test_data_returns_reference_layout(fava, tmp_path):
     assert m.data("no such field") is None
 
 
-@pytest.mark.parametrize("mode", ["native", "hybrid"])
 @pytest.mark.parametrize("n,dtype", [(64, np.float32), (256, np.float64), (512, np.float32)])
-def test_native_fft_path_matches_cufft_path(cuda_device, monkeypatch, n, dtype, mode):
+def test_native_fft_path_matches_cufft_path(cuda_device, monkeypatch, n, dtype):
     """FAVA_FFT=native routes power-of-two grids through the hand-written line FFTs (x pass fused with the
-    weighting and fed by TMA bulk copies, strided y pass, disc-pruned z pass) instead of cuFFT; FAVA_FFT=hybrid keeps
-    the fused x pass and hands the (z, y) passes to one cuFFT plan.  Same spectra to 1e-13."""
+    weighting and fed by TMA bulk copies, strided y pass, disc-pruned z pass) instead of cuFFT.  Same spectra to 1e-13."""
     import torch
 
     from fava_b200 import _lib, device
 
-    monkeypatch.setenv("FAVA_FFT", mode)
-    assert _lib.load().fava_fft_native_supported(n) == (1 if mode == "native" else 0)
-    assert _lib.load().fava_fft_native_supported(96) == 0
+    monkeypatch.setenv("FAVA_FFT", "native")
+    assert _lib.load().fava_fft_native_supported(n) == 1 and _lib.load().fava_fft_native_supported(96) == 0
     g = torch.Generator(device=cuda_device)
     g.manual_seed(n)
     tdt = torch.float64 if dtype == np.float64 else torch.float32

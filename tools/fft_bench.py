@@ -41,8 +41,6 @@ def main():
         t = timeit(lambda: device.fft_x_weight3(*f, *w))
         print(f"FFT n={n} x_weight3 [{threads}] (3 comps): {t:.3f} ms  {(32 + 24.05) * n**3 * gb / t * 1e3:.0f} GB/s")
     os.environ.pop("FAVA_FFT_X_THREADS", None)
-    t = timeit(lambda: device.fft_zy(w[0], n, nxh, dev))
-    print(f"cuFFT (z,y) rank-2 strided plan (1 comp): {t:.3f} ms  {4 * 16 * n * n * nxh * gb / t * 1e3:.0f} GB/s (two passes' bytes)")
     t = timeit(lambda: device.fft_cols(w[0], n, nxh, n, dev))
     print(f"FFT n={n} cols y (1 comp): {t:.3f} ms  {2 * 16 * n * n * nxh * gb / t * 1e3:.0f} GB/s")
     t = timeit(lambda: device.fft_cols(w[0], n, n * nxh, 1, dev, prune_grid_n=n))
