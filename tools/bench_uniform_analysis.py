@@ -25,7 +25,8 @@ def main():
     out = {"peak_gbs": peak, "kernels": {}}
     g = torch.Generator(device=dev)
     g.manual_seed(5)
-    for n, dt in ((1024, torch.float32), (512, torch.float64), (768, torch.float64)):
+    quick = "quick" in sys.argv[1:]  # one size only (used under ncu)
+    for n, dt in ((1024, torch.float32),) if quick else ((1024, torch.float32), (512, torch.float64), (768, torch.float64)):
         if n % 2 ** (ua.box_levels((n, n, n)) - 1):
             tiles_only = True  # 768 is not a multiple of 512: time the tile kernel alone
         else:
@@ -56,6 +57,9 @@ def main():
                     "note": "counts.zero_ + fava_fractal_tiles" + ("" if tiles_only else " + fava_fractal_coarse")}
         os.environ.pop("FAVA_FRACTAL_CTA", None)
         del f, sheet
+    if quick:
+        print(json.dumps(out))
+        return
     n = 512
     vel = [torch.rand((n, n, n), generator=g, device=dev, dtype=torch.float32) for _ in range(3)]
     nsep, npts = 100, 10000
