@@ -77,7 +77,7 @@ template <typename T, int kThreads, int kMinCtas>
 __global__ void __launch_bounds__(kThreads, kMinCtas)
 k_fractal_tiles(const T* __restrict__ f, int64_t nz, int64_t ny, int64_t nx, int64_t zf0, int64_t tz0, double c,
                 unsigned long long* __restrict__ counts, uint8_t* __restrict__ coarse) {
-    __shared__ uint32_t s_lt[kHalo * kHalo], s_gt[kHalo * kHalo];  // [z + 1][y + 1], halo rows included
+    __shared__ uint2 s_lg[kHalo * kHalo];  // (lt, gt) words of row [z + 1][y + 1], halo rows included
     __shared__ uint32_t s_flag[kTile * kTile], s_cand[kTile * kTile];  // [z][y]
     __shared__ uint16_t s_rows[kTile * kTile];  // rows holding candidates (any order)
     __shared__ int cnt[kTileLevels], s_nrows;
@@ -103,24 +103,25 @@ k_fractal_tiles(const T* __restrict__ f, int64_t nz, int64_t ny, int64_t nx, int
         uint32_t we = 0;
         if ((wl | wg) != 0xffffffffu) we = __ballot_sync(0xffffffffu, !lt && !gt && v == v);  // warp-uniform
         if (lane == 0) {
-            s_lt[zzi * kHalo + yyi] = wl;
-            s_gt[zzi * kHalo + yyi] = wg;
+            s_lg[zzi * kHalo + yyi] = make_uint2(wl, wg);  // one 64-bit store
             if (zzi >= 1 && zzi <= kTile && yyi >= 1 && yyi <= kTile) s_flag[(zzi - 1) * kTile + (yyi - 1)] = we;
         }
     };
     constexpr int kBatch = sizeof(T) == 4 ? 12 : 9;
+    // halo-inclusive plane indices zzi in [zz_lo, zz_hi) exist in the domain (plane zt - 1 + zzi)
+    const int zz_lo = zt == 0 ? 1 : 0, zz_hi = (int)min((int64_t)kHalo, nz - zt + 1);
 #pragma unroll 1
     for (int yyi = warp + 1; yyi <= kTile; yyi += kWarps) {  // z-march over the tile's own y rows
         const int64_t y = y0 + yyi - 1;
         const bool ok = x_in && y < ny;
-        const T* p = base + ((zt - 1) * ny + y) * nx + x0 + lane;  // row (y, zt - 1); dereferenced only when valid
+        const T* q = base + ((zt - 1) * ny + y) * nx + x0 + lane;  // row (y, zt - 1); dereferenced only when valid
 #pragma unroll 1
         for (int zb = 0; zb < kHalo; zb += kBatch) {
             T v[kBatch];
 #pragma unroll
             for (int b = 0; b < kBatch; ++b) {
-                const int64_t z = zt - 1 + zb + b;
-                v[b] = (ok && zb + b < kHalo && z >= 0 && z < nz) ? __ldg(p + (int64_t)(zb + b) * plane) : tnan;
+                v[b] = (ok && zb + b >= zz_lo && zb + b < zz_hi) ? __ldg(q) : tnan;
+                q += plane;
             }
 #pragma unroll
             for (int b = 0; b < kBatch; ++b)
@@ -154,7 +155,7 @@ k_fractal_tiles(const T* __restrict__ f, int64_t nz, int64_t ny, int64_t nx, int
         uint32_t cand = 0;
         if (z < nz && y < ny) {
             const int h = (zz + 1) * kHalo + (yy + 1);
-            const uint32_t l = s_lt[h], g = s_gt[h];
+            const uint32_t l = s_lg[h].x, g = s_lg[h].y;
             const T* rowp = base + (z * ny + y) * nx + x0;
             const T vl = x0 >= 1 ? __ldg(rowp - 1) : tnan;  // the row's two x-halo cells
             const T vr = x0 + kTile < nx ? __ldg(rowp + kTile) : tnan;
@@ -163,7 +164,7 @@ k_fractal_tiles(const T* __restrict__ f, int64_t nz, int64_t ny, int64_t nx, int
             if (yv && zv) {
                 // low visited cells with a high neighbour
                 const uint32_t g_any = (g >> 1) | (side.gt(vr) ? 0x80000000u : 0u) | (g << 1) | (side.gt(vl) ? 1u : 0u) |
-                                       s_gt[h + 1] | s_gt[h - 1] | s_gt[h + kHalo] | s_gt[h - kHalo];
+                                       s_lg[h + 1].y | s_lg[h - 1].y | s_lg[h + kHalo].y | s_lg[h - kHalo].y;
                 cand = l & xvis & g_any;
             }
             // high cells with a low visited neighbour
@@ -173,10 +174,10 @@ k_fractal_tiles(const T* __restrict__ f, int64_t nz, int64_t ny, int64_t nx, int
                 l_vis = (lx >> 1) | ((xvis_right && side.lt(vr)) ? 0x80000000u : 0u) | (lx << 1) |
                         ((xvis_left && side.lt(vl)) ? 1u : 0u);
             }
-            if (yv_p && zv) l_vis |= s_lt[h + 1] & xvis;
-            if (yv_m && zv) l_vis |= s_lt[h - 1] & xvis;
-            if (yv && zv_p) l_vis |= s_lt[h + kHalo] & xvis;
-            if (yv && zv_m) l_vis |= s_lt[h - kHalo] & xvis;
+            if (yv_p && zv) l_vis |= s_lg[h + 1].x & xvis;
+            if (yv_m && zv) l_vis |= s_lg[h - 1].x & xvis;
+            if (yv && zv_p) l_vis |= s_lg[h + kHalo].x & xvis;
+            if (yv && zv_m) l_vis |= s_lg[h - kHalo].x & xvis;
             cand |= g & l_vis;
         }
         s_cand[row] = cand;
