@@ -60,45 +60,6 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// Row-walking form of K4: a CTA takes whole rows (grid-stride), a thread owns U pairs 256 apart in the row, so the
-// index arithmetic has no 64-bit division and 4*U independent 16-byte loads are in flight per thread before the first
-// store; outputs are streaming stores (the transform reads them next, nothing else does).
-template <typename T, int U>
-__global__ void __launch_bounds__(256)
-    k_ke_weight3_rows(const T* __restrict__ rho, const T* __restrict__ ux, const T* __restrict__ uy,
-                      const T* __restrict__ uz, int64_t nrows, int64_t nx, int64_t pitch, double* __restrict__ wx,
-                      double* __restrict__ wy, double* __restrict__ wz) {
-    const int half = (int)(nx >> 1);
-    for (int64_t row = blockIdx.x; row < nrows; row += gridDim.x) {
-        const int64_t in0 = row * nx, out0 = row * pitch;
-        for (int p0 = threadIdx.x; p0 < half; p0 += 256 * U) {
-            double r[U][2], a[U][2], b[U][2], c[U][2];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int p = p0 + 256 * u;
-                if (p < half) {
-                    const int64_t in = in0 + 2 * p;
-                    VecLoad<T, 2>::ld(rho + in, r[u]);
-                    VecLoad<T, 2>::ld(ux + in, a[u]);
-                    VecLoad<T, 2>::ld(uy + in, b[u]);
-                    VecLoad<T, 2>::ld(uz + in, c[u]);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int p = p0 + 256 * u;
-                if (p < half) {
-                    const int64_t out = out0 + 2 * p;
-                    const double s0 = sqrt(r[u][0]), s1 = sqrt(r[u][1]);
-                    __stcs(reinterpret_cast<double2*>(wx + out), make_double2(s0 * a[u][0], s1 * a[u][1]));
-                    __stcs(reinterpret_cast<double2*>(wy + out), make_double2(s0 * b[u][0], s1 * b[u][1]));
-                    __stcs(reinterpret_cast<double2*>(wz + out), make_double2(s0 * c[u][0], s1 * c[u][1]));
-                }
-            }
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // K6: power, projection and shell binning
 // ------------------------------------------------------------------------------------------------
@@ -409,19 +370,6 @@ int fava_ke_weight3(fava_ctx* ctx, const void* d_rho, const void* d_ux, const vo
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t npairs = nrows * (nx / 2);
     const unsigned grid = (unsigned)std::min<int64_t>((npairs + 255) / 256, (int64_t)ctx->num_sms * 32);
-    // FAVA_K4=rows: the row-walking kernel (experimental until measured; csrc/spectrum.cu)
-    const char* k4 = getenv("FAVA_K4");
-    if (k4 && k4[0] == 'r' && nx >= 512) {
-        const unsigned rgrid = (unsigned)std::min<int64_t>(nrows, (int64_t)ctx->num_sms * 16);
-        if (dtype == FAVA_F64)
-            k_ke_weight3_rows<double, 2><<<rgrid, 256, 0, st>>>((const double*)d_rho, (const double*)d_ux, (const double*)d_uy,
-                                                                (const double*)d_uz, nrows, nx, pitch, d_wx, d_wy, d_wz);
-        else
-            k_ke_weight3_rows<float, 2><<<rgrid, 256, 0, st>>>((const float*)d_rho, (const float*)d_ux, (const float*)d_uy,
-                                                               (const float*)d_uz, nrows, nx, pitch, d_wx, d_wy, d_wz);
-        FAVA_LAUNCHED();
-        return FAVA_OK;
-    }
     if (dtype == FAVA_F64)
         k_ke_weight3<double><<<grid, 256, 0, st>>>((const double*)d_rho, (const double*)d_ux, (const double*)d_uy,
                                                    (const double*)d_uz, nrows, nx, pitch, d_wx, d_wy, d_wz);

@@ -326,33 +326,6 @@ def test_fft_x_pass_odd_row_count_and_small_grids(cuda_device):
             assert err <= 1e-13, (nrows, c, err)
 
 
-@pytest.mark.parametrize("shape,dtype", [((2, 8, 1024), "float64"), ((3, 5, 512), "float32"), ((1, 7, 1536), "float64")])
-def test_k4_row_walking_variant_writes_identical_bytes(cuda_device, monkeypatch, shape, dtype):
-    """FAVA_K4=rows (row-walking weighting kernel, no index division, streaming stores) against the default kernel."""
-    import torch
-
-    from fava_b200 import device
-
-    nz, ny, nx = shape
-    pitch = 2 * (nx // 2 + 1)
-    g = torch.Generator(device=cuda_device)
-    g.manual_seed(nx)
-    f = [(torch.rand(shape, generator=g, device=cuda_device, dtype=torch.float64) + 0.25).to(getattr(torch, dtype)) for _ in range(4)]
-    outs = {}
-    for mode in ("pairs", "rows"):
-        if mode == "rows":
-            monkeypatch.setenv("FAVA_K4", "rows")
-        w = [torch.full((nz * ny, pitch), -7.0, dtype=torch.float64, device=cuda_device) for _ in range(3)]
-        device.ke_weight3(*f, *[t.data_ptr() for t in w])
-        torch.cuda.synchronize()
-        outs[mode] = w
-    for a, b in zip(outs["pairs"], outs["rows"]):
-        assert torch.equal(a, b)
-        assert bool((a[:, nx:] == -7.0).all())  # the padding columns stay untouched
-    ref = torch.sqrt(f[0].double()) * f[2].double()
-    assert torch.equal(outs["rows"][1][:, :nx].reshape(shape), ref)
-
-
 def test_staging_file_and_host_paths_are_byte_exact(cuda_device, tmp_path):
     """fava_stage_h2d (pread -> pinned ring -> async H2D) and fava_stage_host_h2d deliver the dataset's bytes
     unchanged, for sizes around the 16 MiB chunk / 2 MiB slice boundaries and odd tails."""
