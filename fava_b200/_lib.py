@@ -67,6 +67,11 @@ SIGNATURES: dict[str, tuple] = {
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_i64, c_i64, c_void_p, c_void_p, c_void_p,
          c_void_p, c_void_p],
     ),
+    "fava_plane_moments_xz_weight3": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_i64, c_i64, c_void_p, c_void_p, c_void_p,
+         c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_void_p],
+    ),
     "fava_plane_moments_blocks": (
         c_int,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_i64, c_i64, c_int,

@@ -130,14 +130,25 @@ def plane_moments(rho, ux, uy, uz, axis: int, pivots: torch.Tensor | None = None
     return out, pivots
 
 
-def plane_moments_xz(rho, ux, uy, uz):
-    """Moments for axis x and axis z from one pass (fava_plane_moments_xz) -> ((mom_x, piv_x), (mom_z, piv_z))."""
+def plane_moments_xz(rho, ux, uy, uz, weighted_out=None):
+    """Moments for axis x and axis z from one pass (fava_plane_moments_xz) -> ((mom_x, piv_x), (mom_z, piv_z)).
+    `weighted_out` = three device addresses: the pass also writes sqrt(rho) u_n there in the row-padded layout of the
+    spectrum's in-place transform (fava_plane_moments_xz_weight3)."""
     nz, ny, nx = _check_fields(rho, ux, uy, uz)
     ctx = get_context(rho.device)
     piv_x = plane_pivots(ux, uy, uz, 0)
     piv_z = plane_pivots(ux, uy, uz, 2)
     mom_x = torch.empty((FAVA_NMOM, nx), dtype=torch.float64, device=rho.device)
     mom_z = torch.empty((FAVA_NMOM, nz), dtype=torch.float64, device=rho.device)
+    if weighted_out is not None:
+        wx, wy, wz = (C.c_void_p(int(p)) for p in weighted_out)
+        _lib.check(
+            ctx.lib.fava_plane_moments_xz_weight3(ctx.handle, _ptr(rho), _ptr(ux), _ptr(uy), _ptr(uz), _dtype_code(rho),
+                                                  nz, ny, nx, _ptr(piv_x), _ptr(piv_z), _ptr(mom_x), _ptr(mom_z),
+                                                  2 * (nx // 2 + 1), wx, wy, wz, _stream(rho)),
+            "fava_plane_moments_xz_weight3",
+        )
+        return (mom_x, piv_x), (mom_z, piv_z)
     _lib.check(
         ctx.lib.fava_plane_moments_xz(ctx.handle, _ptr(rho), _ptr(ux), _ptr(uy), _ptr(uz), _dtype_code(rho), nz, ny, nx,
                                       _ptr(piv_x), _ptr(piv_z), _ptr(mom_x), _ptr(mom_z), _stream(rho)),

@@ -139,14 +139,18 @@ def spectral_buffers(n: int, nz_local: int, dev) -> list[int]:
     return _plan(n, dist.rank(), world, dev).send
 
 
-def spectrum_from_transformed_slabs(n: int, dev, epilogue=None) -> dict[str, np.ndarray]:
+def spectrum_from_transformed_slabs(n: int, dev, epilogue=None, xy_done: bool = True) -> dict[str, np.ndarray]:
     """Rest of the spectrum once `spectral_buffers` hold the 2-D transforms of this rank's planes (filled chunk
-    by chunk while the slab was still arriving from the host, stats.host_step): exchange, z transforms, binning."""
+    by chunk while the slab was still arriving from the host, stats.host_step): exchange, z transforms, binning.
+    `xy_done=False` (single rank): the buffers hold the weighted real fields only (written by the fused moment pass)
+    and the 2-D transforms run here first."""
     if dist.world_size() > 1:
         return slab_ke_spectrum(None, None, None, None, n, epilogue=epilogue, xy_done=True, dev=dev)
     w = spectral_buffers(n, n, dev)
     sums = torch.zeros((3, n // 2 - 1), dtype=torch.float64, device=dev)
     for c in range(3):
+        if not xy_done:
+            device.fft_xy(w[c], n, n, n, dev)
         device.fft_z(w[c], n, n * (n // 2 + 1), dev)
     device.spectrum_bin(w[0], w[1], w[2], n, n, None, None, sums)
     if epilogue is not None:

@@ -121,12 +121,29 @@ def slab_step(rho, ux, uy, uz, n: int, cell_volume: float, layer_volume: float, 
             mom, piv = pending[ax]
             out[ax] = slab_profiles_finish(mom, piv, ax, cell_volume, layer_volume, favre=favre, gather=False)
 
-    if spectrum:
+    if spectrum and fuse_weighting(rho, axes, n):
+        # one rank, profiles + spectrum: the x/z moment pass also writes sqrt(rho) u_n for the transform, so the
+        # spectrum does not read rho,ux,uy,uz again (EXPERIMENTAL: opt-in with FAVA_FUSE_K4=1)
+        w = spec.spectral_buffers(n, n, rho.device)
+        pending[0], pending[2] = device.plane_moments_xz(rho, ux, uy, uz, weighted_out=w)
+        if 1 in axes:
+            pending[1] = slab_moments_local(rho, ux, uy, uz, 1)
+        out["spectrum"] = spec.spectrum_from_transformed_slabs(n, rho.device, epilogue=finish_profiles, xy_done=False)
+    elif spectrum:
         out["spectrum"] = spec.slab_ke_spectrum(rho, ux, uy, uz, n, overlap=pieces, epilogue=finish_profiles)
     else:
         local_moments()
         finish_profiles()
     return out
+
+
+def fuse_weighting(rho, axes, n: int) -> bool:
+    """Whether `slab_step` lets the x/z moment pass write the spectrum's weighted fields (one rank, cubic even grid,
+    x and z profiles requested, FAVA_FUSE_K4=1)."""
+    import os
+
+    return (os.environ.get("FAVA_FUSE_K4") == "1" and dist.world_size() == 1 and 0 in axes and 2 in axes
+            and tuple(rho.shape) == (n, n, n) and n % 2 == 0)
 
 
 def host_step(host, n: int, cell_volume: float, layer_volume: float, axes=(0, 1, 2), spectrum: bool = True,

@@ -94,6 +94,14 @@ int fava_plane_moments(fava_ctx* ctx, const void* d_rho, const void* d_ux, const
 int fava_plane_moments_xz(fava_ctx* ctx, const void* d_rho, const void* d_ux, const void* d_uy, const void* d_uz,
                           int dtype, int64_t nz, int64_t ny, int64_t nx, const double* d_piv_x,
                           const double* d_piv_z, double* d_mom_x, double* d_mom_z, void* stream);
+/* fava_plane_moments_xz that also writes K4's output (fava_ke_weight3: w_n = sqrt(rho) u_n, rows of `pitch` doubles,
+ * FlashUniform.py:266-268) from the values it has in registers, so that a step computing profiles AND the spectrum
+ * reads rho,ux,uy,uz once less.  Needs an even nx and 16-byte aligned fields / outputs.  EXPERIMENTAL in round 1:
+ * compiled and parity-tested behind FAVA_FUSE_K4=1, not the default path yet. */
+int fava_plane_moments_xz_weight3(fava_ctx* ctx, const void* d_rho, const void* d_ux, const void* d_uy,
+                                  const void* d_uz, int dtype, int64_t nz, int64_t ny, int64_t nx,
+                                  const double* d_piv_x, const double* d_piv_z, double* d_mom_x, double* d_mom_z,
+                                  int64_t pitch, double* d_wx, double* d_wy, double* d_wz, void* stream);
 
 /* Block-list front end for FLASH block datasets [nblocks][nzb][nyb][nxb] (AMR or multi-block
  * uniform plt files).  For leaf l of the table: planes i=0..nrb-1 of block blk[l] normal to `axis`
