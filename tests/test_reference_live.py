@@ -157,3 +157,21 @@ def test_structure_functions_reference_equals_oracle_with_wrapping(tmp_path):
             assert np.array_equal(ref[kind][o], got[kind][o]), (kind, o)
     with pytest.raises(ValueError):
         m.structure_functions()  # default sep_bounds [0, 1] with log_scale: np.geomspace refuses 0
+
+
+def test_flame_window_fit_equals_reference():
+    """§8f rank 3: the flame-brush centre (Levenberg-Marquardt super-Gaussian fit of Ryy + Rzz, _flash.py:1613-1659),
+    with and without a mask — host-only SciPy in both implementations."""
+    import fava_b200
+
+    RefAMR, _, _ = rh.ref_modules()
+    rng = np.random.default_rng(3)
+    x = (np.arange(96) + 0.5) * 1.0e5 - 20.0e5
+    bump = np.exp(-2.0 * ((x - 12.0e5) / 9.0e5) ** 10)
+    stress = {k: (3.0e7 * bump * (1.0 + 0.05 * rng.random(x.size)) + 1.0e3) for k in ("Rxx", "Ryy", "Rzz")}
+    mask = np.flatnonzero((x > -5.0e5) & (x < 40.0e5))
+    ours, ref = fava_b200.mesh.FLASH(None), RefAMR(None)
+    for m in (None, mask):
+        a = ours.flame_window(x.copy(), {k: v.copy() for k, v in stress.items()}, m)
+        b = ref.flame_window(x.copy(), {k: v.copy() for k, v in stress.items()}, m)
+        assert a == b and 5.0e5 < a < 20.0e5, (a, b)
