@@ -97,12 +97,31 @@ def uniform_analysis_cases(tmp):
         save(f"g6_uniform_analysis_{n}", **o)
 
 
+def slice_cases(tmp):
+    """G7: slice_integral / slice_average of the reference (axis 0) on an AMR plt file."""
+    RefAMR, _, _ = rh.ref_modules()
+    mesh = synth.octree_mesh((2, 1, 2), (4, 8, 4), 3, seed=71, p_refine=0.5, bounds=((0.0, 2.0), (-1.0, 1.0), (0.0, 1.0)))
+    fields = synth.block_fields(mesh, names=FIELDS, dtype=np.float32, seed=71)
+    p = tmp / "g7_hdf5_plt_cnt_0000"
+    synth.write_flash_file(p, mesh, fields)
+    m = RefAMR(str(p))
+    m.load()
+    out = {f"in_{k}": v for k, v in fields.items()}
+    out.update({f"mesh_{k}": v for k, v in mesh_arrays(mesh).items()})
+    out["span"], out["integral_dens"] = (np.array(v) for v in m.slice_integral("dens", axis=0))
+    out["average_velx"] = np.array(m.slice_average("velx", axis=0)[1])
+    save("g7_slice_integral", **out)
+
+
 def main():
     if not rh.reference_available():
         raise SystemExit("the reference is not mounted; goldens can only be generated in the build container")
     tmp = Path(tempfile.mkdtemp(prefix="fava_golden_"))
-    if "g6" in sys.argv[1:]:  # only the uniform-analysis vectors
-        uniform_analysis_cases(tmp)
+    if "g6" in sys.argv[1:] or "g7" in sys.argv[1:]:  # only the vectors added after the first batch
+        if "g6" in sys.argv[1:]:
+            uniform_analysis_cases(tmp)
+        if "g7" in sys.argv[1:]:
+            slice_cases(tmp)
         return
 
     # G1: config 1 in miniature — uniform single-block plt (f32), 32x24x16 cells, non-cubic extent
@@ -173,6 +192,7 @@ def main():
         save(f"g5_spectrum_{n}", **o)
 
     uniform_analysis_cases(tmp)
+    slice_cases(tmp)
 
 
 if __name__ == "__main__":

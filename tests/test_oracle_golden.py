@@ -109,3 +109,13 @@ def test_kinetic_energy_single_mode_known_answer():
     expect = np.zeros(n // 2 - 1)
     expect[m] = 4 * np.pi * m**2 * (2 * 0.5 * 0.25) / count
     maxnorm_close(sp["total"], expect, 1e-13, "single-mode total")
+
+
+def test_slice_integral_and_average_bit_exact():
+    """§8f rank 1: oracle == the reference's slice_integral / slice_average (axis 0) on the G7 AMR file."""
+    g = load_golden("g7_slice_integral")
+    mesh = golden_mesh(g)
+    geom, data = oracle_geom(mesh), oracle_data(golden_fields(g))
+    span, alp = orc.slice_integral(geom, data["dens"], 0)
+    assert np.array_equal(span, g["span"]) and np.array_equal(alp, g["integral_dens"])
+    assert np.array_equal(orc.slice_average(geom, data["velx"], 0)[1], g["average_velx"])

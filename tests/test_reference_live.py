@@ -175,3 +175,26 @@ def test_flame_window_fit_equals_reference():
         a = ours.flame_window(x.copy(), {k: v.copy() for k, v in stress.items()}, m)
         b = ref.flame_window(x.copy(), {k: v.copy() for k, v in stress.items()}, m)
         assert a == b and 5.0e5 < a < 20.0e5, (a, b)
+
+
+@pytest.mark.parametrize("seed,levels", [(71, 3), (72, 1)])
+def test_slice_integral_and_average_reference_equal_oracle(tmp_path, seed, levels):
+    """§8f rank 1 (axis 0, the axis the reference reduces correctly): plane integral / average of a field over the
+    leaves of an AMR file, _flash.py:1427-1504."""
+    mesh = synth.octree_mesh((2, 1, 2), (4, 8, 4), levels, seed=seed, p_refine=0.5, bounds=((0.0, 2.0), (-1.0, 1.0), (0.0, 1.0)))
+    fields = synth.block_fields(mesh, names=FIELDS, dtype=np.float32, seed=seed)
+    p = tmp_path / "si_hdf5_plt_cnt_0000"
+    synth.write_flash_file(p, mesh, fields)
+    RefAMR, _, _ = rh.ref_modules()
+    m = RefAMR(str(p))
+    m.load()
+    geom, data = oracle_geom(mesh), oracle_data(fields)
+    span, alp = m.slice_integral("dens", axis=0)
+    s0, a0 = orc.slice_integral(geom, data["dens"], 0)
+    assert np.array_equal(span, s0) and np.array_equal(alp, a0)
+    try:
+        span, avg = m.slice_average("velx", axis=0)
+    except Exception as exc:  # the reference forwards an Enum as array index; record rather than hide a change there
+        pytest.skip(f"reference slice_average raises: {exc!r}")
+    s1, v1 = orc.slice_average(geom, data["velx"], 0)
+    assert np.array_equal(span, s1) and np.array_equal(avg, v1)
