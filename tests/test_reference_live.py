@@ -198,3 +198,64 @@ def test_slice_integral_and_average_reference_equal_oracle(tmp_path, seed, level
         pytest.skip(f"reference slice_average raises: {exc!r}")
     s1, v1 = orc.slice_average(geom, data["velx"], 0)
     assert np.array_equal(span, s1) and np.array_equal(avg, v1)
+
+
+def test_model_file_discovery_equals_reference(tmp_path):
+    """fava.FLASH(directory): the five file tables ("by number" / "by index"), nfiles() and convert_filename_type
+    (fava/model/flash.py:28-82, :153-169) against the reference's model on the same directory."""
+    import fava_b200
+
+    _, _, ref_fava = rh.ref_modules()
+    names = ["r_hdf5_plt_cnt_0000", "r_hdf5_plt_cnt_0010", "r_hdf5_plt_cnt_0003", "r_hdf5_chk_0002", "r_hdf5_uniform_0010",
+             "r_hdf5_analysis_0003", "r_hdf5_part_0001", "r_hdf5_plt_cnt_00100", "notes.txt", "r_forced_hdf5_plt_cnt_0001"]
+    for nme in names:
+        (tmp_path / nme).write_bytes(b"")
+    ours, ref = fava_b200.FLASH(tmp_path), ref_fava.FLASH(tmp_path)
+    for table in ("chk_files", "plt_files", "prt_files", "uni_files", "anl_files"):
+        a, b = getattr(ours, table), getattr(ref, table)
+        for key in ("by number", "by index"):
+            assert {k: p.name for k, p in a[key].items()} == {k: p.name for k, p in b[key].items()}, (table, key)
+    for ft in ("chk", "plt", "prt", "uni", "anl"):
+        assert ours.nfiles(file_type=ft) == ref.nfiles(file_type=ft), ft
+
+
+def test_mesh_metadata_after_load_equals_reference(tmp_path):
+    """A2: FLASH.load / FlashUniform.load — every attribute the reference sets from the file's tables and the derived
+    geometry helpers (_flash.py:106-163, :370-411, :583-617, :914-953; FlashUniform.py:37-83)."""
+    import fava_b200
+
+    RefAMR, RefUniform, _ = rh.ref_modules()
+    mesh = synth.octree_mesh((2, 1, 2), (4, 8, 4), 3, seed=9, p_refine=0.5, bounds=((0.0, 2.0), (-1.0, 1.0), (0.5, 1.0)))
+    fields = synth.block_fields(mesh, names=FIELDS + ("pres",), dtype=np.float32, seed=9)
+    p = tmp_path / "md_hdf5_plt_cnt_0004"
+    synth.write_flash_file(p, mesh, fields, time=0.75)
+    ours, ref = fava_b200.mesh.FLASH(p), RefAMR(str(p))
+    ours.load()
+    ref.load()
+    scalars = ("ndim", "nxb", "nyb", "nzb", "nblocks", "nblockx", "nblocky", "nblockz", "xmin", "xmax", "ymin", "ymax", "zmin",
+               "zmax", "time", "refine_level_max", "domain_volume", "ncells")
+    for name in scalars:
+        assert getattr(ours, name) == getattr(ref, name), name
+    arrays = ("domain_bounds", "nCellsVec", "nBlksVec", "block_bounds", "refine_level", "node_type", "gid", "which_child",
+              "coordinates", "block_size")
+    for name in arrays:
+        a, b = np.asarray(getattr(ours, name)), np.asarray(getattr(ref, name))
+        assert a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b), name
+    assert [str(f) for f in ours.fields] == [str(f) for f in ref.fields]
+    assert np.array_equal(ours.get_blocklist(), ref.get_blocklist())
+    assert np.array_equal(ours.get_cell_volumes(), ref.get_cell_volumes())
+    for axis in range(3):
+        assert ours.get_minimum_deltas(axis) == ref.get_minimum_deltas(axis)
+        assert np.array_equal(ours.get_delta_from_refine_level(axis, ours.refine_level), ref.get_delta_from_refine_level(axis, ref.refine_level))
+    # uniform 3-D file
+    shape = (8, 12, 16)
+    f = synth.uniform_fields(shape, names=FIELDS, dtype=np.float32, seed=4)
+    pu = tmp_path / "md_hdf5_uniform_0004"
+    synth.write_flash_file(pu, synth.single_block_mesh(shape, ((0.0, 2.0), (0.0, 1.0), (-1.0, 1.0))), f, uniform3d=True, time=0.5)
+    ou, ru = fava_b200.mesh.FlashUniform(pu), RefUniform(str(pu))
+    ou.load()
+    ru.load()
+    for name in ("ndim", "nxb", "nyb", "nzb", "nblocks", "xmin", "xmax", "ymin", "ymax", "zmin", "zmax", "time"):
+        assert getattr(ou, name) == getattr(ru, name), name
+    assert np.array_equal(ou.nCellsVec, ru.nCellsVec) and np.array_equal(ou.domain_bounds, ru.domain_bounds)
+    assert np.array_equal(np.asarray(ou.block_bounds), np.asarray(ru.block_bounds))
