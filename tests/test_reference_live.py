@@ -259,3 +259,43 @@ def test_mesh_metadata_after_load_equals_reference(tmp_path):
         assert getattr(ou, name) == getattr(ru, name), name
     assert np.array_equal(ou.nCellsVec, ru.nCellsVec) and np.array_equal(ou.domain_bounds, ru.domain_bounds)
     assert np.array_equal(np.asarray(ou.block_bounds), np.asarray(ru.block_bounds))
+
+
+def test_pipeline_settings_and_checkpoint_equal_reference(tmp_path, monkeypatch):
+    """§8f rank 3: `Pipeline.restart()` (settings validation, checkpoint pick-up) and `.checkpoint()` write the same
+    `fava.checkpoint` as the reference's driver (fava/__main__.py:22-74) for the same settings and progress."""
+    import importlib.util
+    import json
+
+    from fava_b200.__main__ import Pipeline
+
+    rh.ref_modules()
+    (tmp_path / "x_hdf5_plt_cnt_0000").write_bytes(b"")
+    settings = {"data folder": str(tmp_path), "output folder": str(tmp_path), "basename": "x", "dimension": 3, "model": "m",
+                "reynolds stress": {"skip": False}, "fractal dimension": {"skip": False, "settings": {"field": "flam", "contours": 0.5}}}
+    (tmp_path / "pipeline_settings.json").write_text(json.dumps(settings))
+    monkeypatch.chdir(tmp_path)  # the reference binds its file names to the working directory at import time
+    spec = importlib.util.spec_from_file_location("ref_fava_main", rh.REFERENCE_ROOT / "fava" / "__main__.py")
+    ref_main = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_main)
+
+    progress = {"reynolds stress": {"index": 2}, "analyze uniform data": {"index": 1, "analysis": "structure functions"}}
+    texts = []
+    for pipe in (ref_main.Pipeline(), Pipeline(tmp_path)):
+        pipe.restart()
+        assert pipe.checkpoint_data["settings"] == settings
+        pipe.checkpoint_data.update(progress)
+        pipe.checkpoint()
+        texts.append((tmp_path / "fava.checkpoint").read_text())
+        (tmp_path / "fava.checkpoint").unlink()
+    assert texts[0] == texts[1]
+    # a checkpoint left by one driver is picked up by the other
+    (tmp_path / "fava.checkpoint").write_text(texts[0])
+    ours = Pipeline(tmp_path)
+    ours.restart()
+    assert ours.checkpoint_data["reynolds stress"] == {"index": 2}
+    bad = dict(settings, dimension="3")
+    (tmp_path / "pipeline_settings.json").write_text(json.dumps(bad))
+    for pipe in (ref_main.Pipeline(), Pipeline(tmp_path)):
+        with pytest.raises(AssertionError):
+            pipe.restart()
