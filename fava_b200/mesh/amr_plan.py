@@ -8,8 +8,6 @@ from __future__ import annotations
 
 import numpy as np
 
-from fava_b200 import device
-
 MESH_MDIM = 3
 
 

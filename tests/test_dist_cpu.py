@@ -4,7 +4,6 @@ tests/test_multigpu.py."""
 import os
 import socket
 
-import numpy as np
 import pytest
 import torch
 import torch.multiprocessing as mp
