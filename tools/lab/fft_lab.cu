@@ -1,0 +1,471 @@
+// Design lab for the strided column transforms (NOT part of libfava_b200): candidate kernels around the
+// register-resident FFT core (csrc/fft_core.cuh), each checked against cuFFT on a small batch and timed at full
+// size, plus "copy-only" builds of the same kernels that isolate the cost of the access pattern.
+//
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -I fava_b200/csrc tools/lab/fft_lab.cu \
+//        -lcufft -o tools/lab/fft_lab
+//   tools/lab/fft_lab [nz_full=1024]
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cufft.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "fft_core.cuh"
+
+using namespace fava::fftc;
+
+#define CK(x)                                                                                     \
+    do {                                                                                          \
+        cudaError_t e_ = (x);                                                                     \
+        if (e_ != cudaSuccess) {                                                                  \
+            printf("CUDA error %s at %s:%d: %s\n", #x, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+            exit(2);                                                                              \
+        }                                                                                         \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------------
+struct Prune {
+    int mode;   // 0 none, 1 y pass (keep output rows ky^2 + kx0^2 <= kmax2), 2 z pass (tile skip + output rows)
+    int kmax2;  // (N/2 - 1.5)^2 rounded down
+    int n;
+};
+
+__device__ __forceinline__ int wavenumber(int k, int n) { return k < n / 2 ? k : k - n; }
+
+template <int LOGN, int C, int MODE>
+__global__ void __launch_bounds__(RegPlan<LOGN>::M1* C, (C >= 8 ? 1 : 2))
+    k_cols_direct(double2* __restrict__ data, int64_t rstride, int64_t bstride, int ntile_cols, int64_t ntiles,
+                  const double2* __restrict__ t1, const double2* __restrict__ t2, Prune pr) {
+    using P = RegPlan<LOGN>;
+    using O = Owner<LOGN>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2* xb = reinterpret_cast<double2*>(smem_raw);
+    const int c = threadIdx.x % C, u = threadIdx.x / C;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t b = t / ntile_cols;
+        const int ct = (int)(t - b * ntile_cols);
+        const int kx0 = ct * C;
+        int base2 = kx0 * kx0;
+        if (pr.mode == 2) {
+            const int ky = wavenumber((int)b, pr.n);
+            base2 += ky * ky;
+            if (base2 > pr.kmax2) continue;
+        }
+        double2* base = data + b * bstride + kx0 + c;
+        double2 v[16];
+#pragma unroll
+        for (int m = 0; m < 16; ++m) v[m] = __ldcs(base + (int64_t)O::in_index(u, m) * rstride);
+        if (MODE == 0) {
+            __syncthreads();  // previous tile's exchange reads are complete
+            fft_regs_full<LOGN, C>(v, u, c, xb, t1, t2);
+        }
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const int k = MODE == 0 ? O::out_freq(u, r) : O::in_index(u, r);
+            bool keep = true;
+            if (pr.mode) {
+                const int w = wavenumber(k, pr.n);
+                keep = w * w + base2 <= pr.kmax2;
+            }
+            if (keep) __stcs(base + (int64_t)k * rstride, v[r]);
+        }
+    }
+}
+
+// ---- TMA-fed persistent variant: next tile lands in shared memory while this one is transformed in registers ----
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    for (unsigned spin = 0; !mbar_try(bar, parity); ++spin)
+        if (spin > (1u << 26)) __trap();  // lab safety: never hang the box
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// LINE_DIM = which tensor dimension the transform runs along (1: y pass, 2: z pass); C = 8, 16 doubles per row
+template <int LOGN, int MODE, int LINE_DIM>
+__global__ void __launch_bounds__(RegPlan<LOGN>::M1 * 8, 1)
+    k_cols_tma(const __grid_constant__ CUtensorMap tmap, double2* __restrict__ data, int64_t rstride, int64_t bstride,
+               int ntile_cols, int64_t ntiles, const double2* __restrict__ t1, const double2* __restrict__ t2, Prune pr) {
+    using P = RegPlan<LOGN>;
+    using O = Owner<LOGN>;
+    constexpr int C = 8, N = P::N;
+    constexpr int BOX = 256;  // rows per TMA box
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    double2* land = reinterpret_cast<double2*>(smem_raw);                          // [N][8] complex, 128 B rows
+    double* xb = reinterpret_cast<double*>(smem_raw + sizeof(double2) * N * C);    // [N][8] doubles
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + sizeof(double2) * N * C + sizeof(double) * N * C);
+    const int c = threadIdx.x % C, u = threadIdx.x / C;
+
+    auto next_tile = [&](int64_t t) {  // first tile >= t that survives the tile-level pruning
+        for (; t < ntiles; t += gridDim.x) {
+            if (pr.mode != 2) break;
+            const int64_t b = t / ntile_cols;
+            const int kx0 = (int)(t - b * ntile_cols) * C;
+            const int ky = wavenumber((int)b, pr.n);
+            if (kx0 * kx0 + ky * ky <= pr.kmax2) break;
+        }
+        return t;
+    };
+    auto issue = [&](int64_t t) {  // one thread
+        const int64_t b = t / ntile_cols;
+        const int ct = (int)(t - b * ntile_cols);
+        mbar_expect_tx(bar, (unsigned)(sizeof(double2) * N * C));
+#pragma unroll
+        for (int i = 0; i < N / BOX; ++i) {
+            if (LINE_DIM == 1) tma_load_3d(land + i * BOX * C, &tmap, ct * 2 * C, i * BOX, (int)b, bar);
+            else tma_load_3d(land + i * BOX * C, &tmap, ct * 2 * C, (int)b, i * BOX, bar);
+        }
+    };
+
+    int64_t t = next_tile(blockIdx.x);
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async;\n" ::: "memory");
+        if (t < ntiles) issue(t);
+    }
+    __syncthreads();
+    unsigned parity = 0;
+    while (t < ntiles) {
+        const int64_t b = t / ntile_cols;
+        const int kx0 = (int)(t - b * ntile_cols) * C;
+        int base2 = kx0 * kx0;
+        if (pr.mode == 2) {
+            const int ky = wavenumber((int)b, pr.n);
+            base2 += ky * ky;
+        }
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+        double2 v[16];
+#pragma unroll
+        for (int m = 0; m < 16; ++m) v[m] = land[O::in_index(u, m) * C + c];
+        __syncthreads();  // landing buffer consumed (and the previous tile's exchange reads are complete)
+        const int64_t tn = next_tile(t + gridDim.x);
+        if (threadIdx.x == 0 && tn < ntiles) issue(tn);
+        if (MODE == 0) fft_regs_half<LOGN, C>(v, u, c, xb, t1, t2);
+        double2* base = data + b * bstride + kx0 + c;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const int k = MODE == 0 ? O::out_freq(u, r) : O::in_index(u, r);
+            bool keep = true;
+            if (pr.mode) {
+                const int w = wavenumber(k, pr.n);
+                keep = w * w + base2 <= pr.kmax2;
+            }
+            if (keep) __stcs(base + (int64_t)k * rstride, v[r]);
+        }
+        t = tn;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_fill(double2* d, int64_t n, uint64_t seed) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t z = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(i + 1);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        d[i] = make_double2((double)(z & 0xffffffffu) / 4294967296.0 - 0.5, (double)(z >> 32) / 4294967296.0 - 0.5);
+    }
+}
+
+template <int LOGN>
+static void make_tables(double2** d_t1, double2** d_t2) {
+    using P = RegPlan<LOGN>;
+    std::vector<double2> t1(P::T1_LEN), t2(P::T2_LEN);
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    for (int q = 0; q < 16; ++q)
+        for (int j = 0; j < P::M1; ++j) {
+            const long double a = -two_pi * (long double)((j * q) % P::N) / (long double)P::N;
+            t1[q * P::M1 + j] = make_double2((double)cosl(a), (double)sinl(a));
+        }
+    for (int q = 0; q < 16; ++q)
+        for (int j = 0; j < P::M2; ++j) {
+            const long double a = -two_pi * (long double)((j * q) % P::M1) / (long double)P::M1;
+            t2[q * P::M2 + j] = make_double2((double)cosl(a), (double)sinl(a));
+        }
+    CK(cudaMalloc(d_t1, sizeof(double2) * t1.size()));
+    CK(cudaMalloc(d_t2, sizeof(double2) * t2.size()));
+    CK(cudaMemcpy(*d_t1, t1.data(), sizeof(double2) * t1.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(*d_t2, t2.data(), sizeof(double2) * t2.size(), cudaMemcpyHostToDevice));
+}
+
+typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiled get_encode() {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) {
+        printf("cuTensorMapEncodeTiled not available\n");
+        exit(2);
+    }
+    return (EncodeTiled)fn;
+}
+
+// data: complex [d2][d1][pitch]; box = 8 complex x 256 along line_dim
+static CUtensorMap make_map(double2* data, int64_t pitch, int64_t d1, int64_t d2, int line_dim) {
+    static EncodeTiled enc = get_encode();
+    CUtensorMap m;
+    cuuint64_t dims[3] = {(cuuint64_t)(2 * pitch), (cuuint64_t)d1, (cuuint64_t)d2};
+    cuuint64_t strides[2] = {(cuuint64_t)(pitch * 16), (cuuint64_t)(pitch * 16 * d1)};
+    cuuint32_t box[3] = {16, line_dim == 1 ? 256u : 1u, line_dim == 2 ? 256u : 1u};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, data, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        printf("cuTensorMapEncodeTiled failed: %d\n", (int)r);
+        exit(2);
+    }
+    return m;
+}
+
+struct Shape {
+    int64_t pitch, d1, d2;  // complex [d2][d1][pitch]
+    int line_dim;           // 1: transform along d1 (y pass), 2: along d2 (z pass)
+    int64_t rstride() const { return line_dim == 1 ? pitch : pitch * d1; }
+    int64_t bstride() const { return line_dim == 1 ? pitch * d1 : pitch; }
+    int64_t nbatch() const { return line_dim == 1 ? d2 : d1; }
+    int64_t elems() const { return pitch * d1 * d2; }
+};
+
+constexpr int LOGN = 10;
+constexpr int N = 1 << LOGN;
+static int g_sms = 148;
+
+template <int C, int MODE>
+static void run_direct(double2* d, const Shape& s, const double2* t1, const double2* t2, Prune pr, int ctas_per_sm) {
+    const int ntc = (N / 2) / C;
+    const int64_t ntiles = s.nbatch() * ntc;
+    const size_t smem = sizeof(double2) * N * C;
+    auto kern = k_cols_direct<LOGN, C, MODE>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (int)std::min<int64_t>(ntiles, (int64_t)g_sms * ctas_per_sm);
+    kern<<<grid, RegPlan<LOGN>::M1 * C, smem>>>(d, s.rstride(), s.bstride(), ntc, ntiles, t1, t2, pr);
+    CK(cudaGetLastError());
+}
+
+template <int MODE>
+static void run_tma(double2* d, const Shape& s, const double2* t1, const double2* t2, Prune pr) {
+    constexpr int C = 8;
+    const int ntc = (N / 2) / C;
+    const int64_t ntiles = s.nbatch() * ntc;
+    const size_t smem = sizeof(double2) * N * C + sizeof(double) * N * C + 64;
+    CUtensorMap map = make_map(d, s.pitch, s.d1, s.d2, s.line_dim);
+    const int grid = (int)std::min<int64_t>(ntiles, (int64_t)g_sms);
+    if (s.line_dim == 1) {
+        auto kern = k_cols_tma<LOGN, MODE, 1>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, RegPlan<LOGN>::M1 * C, smem>>>(map, d, s.rstride(), s.bstride(), ntc, ntiles, t1, t2, pr);
+    } else {
+        auto kern = k_cols_tma<LOGN, MODE, 2>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, RegPlan<LOGN>::M1 * C, smem>>>(map, d, s.rstride(), s.bstride(), ntc, ntiles, t1, t2, pr);
+    }
+    CK(cudaGetLastError());
+}
+
+static void cufft_ref(double2* d, const Shape& s) {  // in place, all columns
+    cufftHandle h;
+    int n[1] = {N};
+    if (s.line_dim == 1) {
+        int embed[1] = {N};
+        if (cufftPlanMany(&h, 1, n, embed, (int)s.pitch, 1, embed, (int)s.pitch, 1, CUFFT_Z2Z, (int)s.pitch) != CUFFT_SUCCESS) exit(3);
+        for (int64_t z = 0; z < s.d2; ++z) {
+            cufftDoubleComplex* p = (cufftDoubleComplex*)(d + z * s.pitch * s.d1);
+            if (cufftExecZ2Z(h, p, p, CUFFT_FORWARD) != CUFFT_SUCCESS) exit(3);
+        }
+    } else {
+        int embed[1] = {N};
+        const int cols = (int)(s.pitch * s.d1);
+        if (cufftPlanMany(&h, 1, n, embed, cols, 1, embed, cols, 1, CUFFT_Z2Z, cols) != CUFFT_SUCCESS) exit(3);
+        if (cufftExecZ2Z(h, (cufftDoubleComplex*)d, (cufftDoubleComplex*)d, CUFFT_FORWARD) != CUFFT_SUCCESS) exit(3);
+    }
+    CK(cudaDeviceSynchronize());
+    cufftDestroy(h);
+}
+
+// max |a - b| over the elements a pruned transform must produce, relative to max |b|
+static double compare(const std::vector<double2>& a, const std::vector<double2>& b, const Shape& s, Prune pr, int C) {
+    double err = 0, ref = 0;
+    const int kmax2 = pr.kmax2;
+    for (int64_t i2 = 0; i2 < s.d2; ++i2)
+        for (int64_t i1 = 0; i1 < s.d1; ++i1)
+            for (int64_t x = 0; x < N / 2; ++x) {
+                const int64_t line = s.line_dim == 1 ? i1 : i2, batch = s.line_dim == 1 ? i2 : i1;
+                if (pr.mode) {
+                    const int kx0 = (int)(x / C) * C;
+                    int w = (int)(line < N / 2 ? line : line - N);
+                    int k2 = w * w + kx0 * kx0;
+                    if (pr.mode == 2) {
+                        const int ky = (int)(batch < N / 2 ? batch : batch - N);
+                        k2 += ky * ky;
+                    }
+                    if (k2 > kmax2) continue;
+                }
+                const int64_t idx = (i2 * s.d1 + i1) * s.pitch + x;
+                err = std::max(err, std::max(fabs(a[idx].x - b[idx].x), fabs(a[idx].y - b[idx].y)));
+                ref = std::max(ref, std::max(fabs(b[idx].x), fabs(b[idx].y)));
+            }
+    return err / ref;
+}
+
+template <typename F>
+static float time_ms(F&& f, int reps = 5) {
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    f();
+    CK(cudaDeviceSynchronize());
+    float best = 1e30f;
+    for (int i = 0; i < reps; ++i) {
+        CK(cudaEventRecord(e0));
+        f();
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        best = std::min(best, ms);
+    }
+    return best;
+}
+
+int main(int argc, char** argv) {
+    const int64_t nfull = argc > 1 ? atoll(argv[1]) : 1024;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, 0));
+    g_sms = prop.multiProcessorCount;
+    printf("device %s, %d SMs\n", prop.name, g_sms);
+    double2 *t1, *t2;
+    make_tables<LOGN>(&t1, &t2);
+    const int kmax2 = N * N / 4 - 3 * N / 2 + 2;
+
+    // ---------------- correctness on small shapes -----------------------------------------------------------
+    for (int pitch : {513, 512}) {
+        for (int line_dim : {1, 2}) {
+            Shape s{pitch, line_dim == 1 ? (int64_t)N : 6, line_dim == 1 ? 3 : (int64_t)N, line_dim};
+            const int64_t ne = s.elems();
+            double2 *d_in, *d_ref, *d_out;
+            CK(cudaMalloc(&d_in, sizeof(double2) * ne));
+            CK(cudaMalloc(&d_ref, sizeof(double2) * ne));
+            CK(cudaMalloc(&d_out, sizeof(double2) * ne));
+            k_fill<<<1024, 256>>>(d_in, ne, 42);
+            CK(cudaMemcpy(d_ref, d_in, sizeof(double2) * ne, cudaMemcpyDeviceToDevice));
+            cufft_ref(d_ref, s);
+            std::vector<double2> h_ref(ne), h_out(ne);
+            CK(cudaMemcpy(h_ref.data(), d_ref, sizeof(double2) * ne, cudaMemcpyDeviceToHost));
+            for (int prm : {0, line_dim}) {
+                Prune pr{prm, kmax2, N};
+                auto check = [&](const char* name, int C, auto&& launch) {
+                    CK(cudaMemcpy(d_out, d_in, sizeof(double2) * ne, cudaMemcpyDeviceToDevice));
+                    launch();
+                    cudaError_t e = cudaDeviceSynchronize();
+                    if (e != cudaSuccess) {
+                        printf("CHECK %-12s pitch %d dim %d prune %d: CUDA error %s\n", name, pitch, line_dim, prm, cudaGetErrorString(e));
+                        exit(4);
+                    }
+                    CK(cudaMemcpy(h_out.data(), d_out, sizeof(double2) * ne, cudaMemcpyDeviceToHost));
+                    const double err = compare(h_out, h_ref, s, pr, C);
+                    printf("CHECK %-12s pitch %d dim %d prune %d: rel err %.3e %s\n", name, pitch, line_dim, prm, err,
+                           err < 1e-13 ? "ok" : "FAIL");
+                };
+                check("direct C8", 8, [&] { run_direct<8, 0>(d_out, s, t1, t2, pr, 1); });
+                check("direct C4", 4, [&] { run_direct<4, 0>(d_out, s, t1, t2, pr, 2); });
+                check("tma C8", 8, [&] { run_tma<0>(d_out, s, t1, t2, pr); });
+            }
+            CK(cudaFree(d_in));
+            CK(cudaFree(d_ref));
+            CK(cudaFree(d_out));
+        }
+    }
+
+    // ---------------- timing at full size ---------------------------------------------------------------------
+    for (int pitch : {513, 512, 520}) {
+        double2* d;
+        const int64_t ne = (int64_t)pitch * N * nfull;
+        CK(cudaMalloc(&d, sizeof(double2) * ne));
+        k_fill<<<4096, 256>>>(d, ne, 7);
+        CK(cudaDeviceSynchronize());
+        const double gb_full = 2.0 * 16.0 * (double)(N / 2) * N * nfull / 1e9;  // read + write of the kx < N/2 columns
+        for (int line_dim : {1, 2}) {
+            Shape s{pitch, line_dim == 1 ? (int64_t)N : nfull, line_dim == 1 ? nfull : (int64_t)N, line_dim};
+            for (int prm : {0, line_dim}) {
+                Prune pr{prm, kmax2, N};
+                auto report = [&](const char* name, float ms) {
+                    printf("TIME pitch %d dim %d prune %d %-16s %8.3f ms  %7.1f GB/s (of the unpruned %0.1f GB)\n", pitch, line_dim,
+                           prm, name, ms, gb_full / (ms * 1e-3), gb_full);
+                    fflush(stdout);
+                };
+                report("direct C8 copy", time_ms([&] { run_direct<8, 1>(d, s, t1, t2, pr, 1); }));
+                report("direct C8 copyx2", time_ms([&] { run_direct<8, 1>(d, s, t1, t2, pr, 2); }));
+                report("direct C4 copy", time_ms([&] { run_direct<4, 1>(d, s, t1, t2, pr, 2); }));
+                report("direct C4 copyx4", time_ms([&] { run_direct<4, 1>(d, s, t1, t2, pr, 4); }));
+                report("tma C8 copy", time_ms([&] { run_tma<1>(d, s, t1, t2, pr); }));
+                report("direct C8 fft", time_ms([&] { run_direct<8, 0>(d, s, t1, t2, pr, 1); }));
+                report("direct C4 fft", time_ms([&] { run_direct<4, 0>(d, s, t1, t2, pr, 2); }));
+                report("tma C8 fft", time_ms([&] { run_tma<0>(d, s, t1, t2, pr); }));
+            }
+            if (pitch == 513 || pitch == 512) {  // cuFFT on the same layout (all `pitch` columns)
+                cufftHandle h;
+                int n[1] = {N}, embed[1] = {N};
+                size_t work = 0;
+                cufftCreate(&h);
+                cufftResult r;
+                if (line_dim == 1) {
+                    long long nn[1] = {N}, em[1] = {N};
+                    r = cufftMakePlanMany64(h, 1, nn, em, pitch, 1, em, pitch, 1, CUFFT_Z2Z, pitch, &work);
+                    (void)n, (void)embed;
+                    if (r == CUFFT_SUCCESS) {
+                        float ms = time_ms([&] {
+                            for (int64_t z = 0; z < nfull; ++z) {
+                                cufftDoubleComplex* p = (cufftDoubleComplex*)(d + z * s.pitch * s.d1);
+                                cufftExecZ2Z(h, p, p, CUFFT_FORWARD);
+                            }
+                        }, 2);
+                        printf("TIME pitch %d dim 1 cuFFT per-plane plans %8.3f ms\n", pitch, ms);
+                    }
+                } else {
+                    long long nn[1] = {N}, em[1] = {N};
+                    const long long cols = (long long)pitch * nfull;
+                    r = cufftMakePlanMany64(h, 1, nn, em, cols, 1, em, cols, 1, CUFFT_Z2Z, cols, &work);
+                    if (r == CUFFT_SUCCESS) {
+                        float ms = time_ms([&] { cufftExecZ2Z(h, (cufftDoubleComplex*)d, (cufftDoubleComplex*)d, CUFFT_FORWARD); }, 3);
+                        printf("TIME pitch %d dim 2 cuFFT strided plan   %8.3f ms  %7.1f GB/s\n", pitch, ms,
+                               2.0 * 16.0 * (double)pitch * N * nfull / 1e9 / (ms * 1e-3));
+                    }
+                }
+                cufftDestroy(h);
+            }
+        }
+        CK(cudaFree(d));
+    }
+    printf("LAB DONE\n");
+    return 0;
+}
