@@ -67,11 +67,6 @@ SIGNATURES: dict[str, tuple] = {
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_i64, c_i64, c_void_p, c_void_p, c_void_p,
          c_void_p, c_void_p],
     ),
-    "fava_plane_moments_xz_weight3": (
-        c_int,
-        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_i64, c_i64, c_void_p, c_void_p, c_void_p,
-         c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_void_p],
-    ),
     "fava_plane_moments_blocks": (
         c_int,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_i64, c_i64, c_int,
@@ -103,22 +98,21 @@ SIGNATURES: dict[str, tuple] = {
          c_void_p],
     ),
     "fava_fft_native_supported": (c_int, [c_i64]),
+    "fava_spectral_pitch": (c_i64, [c_i64]),
+    "fava_ke_transform_x": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_i64, c_void_p, c_void_p, c_void_p, c_void_p],
+    ),
+    "fava_ke_transform_y": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_void_p]),
+    "fava_ke_transform_z": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_void_p]),
     "fava_fft_x_weight3": (
         c_int,
-        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_i64, c_void_p, c_void_p, c_void_p, c_void_p],
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_i64, c_i64, c_void_p, c_void_p, c_void_p,
+         c_void_p],
     ),
-    "fava_fft_cols": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_void_p, c_void_p]),
-    "fava_fft_xy": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p]),
-    "fava_ke_weight_fft_xy": (
-        c_int,
-        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_i64, c_void_p, c_void_p, c_void_p, c_void_p],
-    ),
-    "fava_fft_z": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_void_p]),
+    "fava_fft_cols": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_void_p, c_void_p]),
+    "fava_reserve_sms": (c_int, [c_void_p, c_int]),
     "fava_a2a_pack": (
-        c_int,
-        [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_i64, c_i64, c_i64, c_void_p],
-    ),
-    "fava_a2a_copy": (
         c_int,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_i64, c_i64, c_i64, c_void_p],
     ),
@@ -153,6 +147,7 @@ SIGNATURES: dict[str, tuple] = {
     "fava_ipc_close": (c_int, [c_void_p]),
 }
 
+ABI_VERSION = 2  # include/fava_b200.h: FAVA_ABI_VERSION
 _lib = None
 
 
@@ -175,8 +170,9 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError here = header/library drift
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.fava_abi_version() != 1:
-        raise RuntimeError(f"libfava_b200 ABI version {lib.fava_abi_version()} != 1")
+    if lib.fava_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"libfava_b200 ABI version {lib.fava_abi_version()} != {ABI_VERSION}: rebuild with "
+                           "`python -m fava_b200.build`")
     _lib = lib
     return lib
 

@@ -1,6 +1,8 @@
 // Shared internals of libfava_b200: context, error reporting, launch accounting, load helpers.
 #pragma once
 
+#include <cuda.h>
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cufft.h>
 #include <stdint.h>
@@ -68,7 +70,10 @@ struct fava_ctx {
     // host copies of the leaf tables whose device CSR tables are cached in WS_ITEMS0 + axis (block_moments.cu)
     std::string item_cache_key[3];
     std::string prolong_cache_key;  // same for the lattice table of fava_prolong (WS_TABLE)
-    std::map<int64_t, void*> twiddles;  // exp(-2 pi i m / N) tables of the native FFT, per N
+    std::map<int64_t, void*> twiddles;  // twiddle tables of the hand-written FFT, per N (fft.cu)
+    // TMA descriptors of the column passes, keyed by (buffer, pitch, d1, d2, line dim / tile shape)
+    std::map<std::tuple<uintptr_t, int64_t, int64_t, int64_t, int>, CUtensorMap> tensor_maps;
+    int reserved_sms = 0;  // SMs the persistent transform kernels leave free for a concurrent exchange kernel
     fava::Staging* staging = nullptr;
 };
 
@@ -77,8 +82,11 @@ namespace fava {
 // Grow-only device workspace owned by the context.
 int ctx_workspace(fava_ctx* ctx, int slot, size_t bytes, void** out);
 
-// native (hand-written) FFT available for this grid size?  (power of two in [64, 4096], not FAVA_FFT=cufft)
+// hand-written FFT path for this grid size?  (power of two in [256, 2048]; other even N use cuFFT)
 bool fft_native_supported(int64_t n);
+
+// SMs a persistent kernel of the transform may occupy
+inline int ctx_sms(const fava_ctx* ctx) { return ctx->num_sms - ctx->reserved_sms > 0 ? ctx->num_sms - ctx->reserved_sms : 1; }
 
 struct DeviceGuard {
     int prev = -1;

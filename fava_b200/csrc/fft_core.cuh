@@ -170,68 +170,141 @@ __device__ __forceinline__ void twiddle2(double2 (&v)[16], int u, const double2*
     }
 }
 
+// Where element index e of this thread's line lives in the exchange buffer.
+//   ColAddr  - C interleaved lines (column passes): word phi(e) C + c; conflict-free for C = 8 (16- and 8-byte words)
+//              and C = 4 (16-byte words).
+//   LineAddr - one line after the other (x pass, lanes run over the element index): word off + skew(e), where the
+//              skew shifts every block of 64 by 4 and every block of 16 by one more; with 8-byte words every access
+//              pattern of the three exchanges is then conflict-free except the mirrored read of the split (2-way on
+//              half of its phases) - checked by enumeration for N = 256 ... 2048 (tools/lab/bank_conflicts.py).
+__host__ __device__ __forceinline__ constexpr int line_skew(int e) { return e + 4 * (e >> 6) + ((e >> 4) & 3); }
+__host__ __device__ constexpr int line_pitch(int n) { return n < 64 ? 68 : (n / 64) * 68; }
+
+template <int C>
+struct ColAddr {
+    int c;
+    __device__ __forceinline__ int operator()(int e) const { return phi(e) * C + c; }
+};
+struct LineAddr {
+    int off;
+    __device__ __forceinline__ int operator()(int e) const { return off + line_skew(e); }
+};
+
+// Who must arrive before exchanged words may be read: the whole CTA when the lines of a tile are interleaved over all
+// warps (column passes), or only the warps of ONE line when a line owns whole warps (x pass) - the lines of a CTA then
+// drift apart and one line's butterflies overlap another line's shared-memory phase.
+struct CtaSync {
+    __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+template <int THREADS>  // threads of one line; `line` < 3 selects the named barrier 1..3 of this line
+struct LineSync {
+    int line;
+    __device__ __forceinline__ void operator()() const {
+        if constexpr (THREADS <= 32) {
+            __syncwarp();
+        } else {  // immediate barrier ids: with a register id ptxas reserves all 16 barriers of the CTA
+            if (line == 0) asm volatile("bar.sync 1, %0;\n" ::"n"(THREADS) : "memory");
+            else if (line == 1) asm volatile("bar.sync 2, %0;\n" ::"n"(THREADS) : "memory");
+            else asm volatile("bar.sync 3, %0;\n" ::"n"(THREADS) : "memory");
+        }
+    }
+};
+
 // Everything between "v holds the inputs of pass 1" and "v holds the outputs": two exchanges through `xb`
-// (complex words, [N][C], 16 N C bytes).  u = thread's index within the line, c = line.  All threads of the CTA
-// must call it (it contains __syncthreads).
-template <int LOGN, int C>
-__device__ __forceinline__ void fft_regs_full(double2 (&v)[16], int u, int c, double2* __restrict__ xb,
-                                              const double2* __restrict__ t1, const double2* __restrict__ t2) {
+// (complex words).  u = thread's index within the line.  All threads that `sync` joins must call it.
+template <int LOGN, class Addr, class Sync = CtaSync>
+__device__ __forceinline__ void fft_regs_full(double2 (&v)[16], int u, const Addr& at, double2* __restrict__ xb,
+                                              const double2* __restrict__ t1, const double2* __restrict__ t2,
+                                              const Sync& sync = Sync()) {
     using P = RegPlan<LOGN>;
     using O = Owner<LOGN>;
     dft16(v);
     twiddle1<LOGN>(v, u, t1);
 #pragma unroll
-    for (int q = 0; q < 16; ++q) xb[phi(O::x1_write(u, q)) * C + c] = v[q];
-    __syncthreads();
+    for (int q = 0; q < 16; ++q) xb[at(O::x1_write(u, q))] = v[q];
+    sync();
 #pragma unroll
-    for (int m = 0; m < 16; ++m) v[m] = xb[phi(O::x1_read(u, m)) * C + c];
+    for (int m = 0; m < 16; ++m) v[m] = xb[at(O::x1_read(u, m))];
     dft16(v);
     if constexpr (P::M2 > 1) {
         twiddle2<LOGN>(v, u, t2);
 #pragma unroll
-        for (int q = 0; q < 16; ++q) xb[phi(O::x2_write(u, q)) * C + c] = v[q];  // own slots: no barrier needed before
-        __syncthreads();
+        for (int q = 0; q < 16; ++q) xb[at(O::x2_write(u, q))] = v[q];  // own slots: no barrier needed before
+        sync();
 #pragma unroll
-        for (int r = 0; r < 16; ++r) v[r] = xb[phi(O::x2_read(u, r)) * C + c];
+        for (int r = 0; r < 16; ++r) v[r] = xb[at(O::x2_read(u, r))];
         dft_groups<P::M2>(v);
     }
 }
 
-// Same with an exchange buffer of half the size ([N][C] doubles, 8 N C bytes): real and imaginary parts go
-// through it one after the other (twice the barriers, same traffic).
-template <int LOGN, int C>
-__device__ __forceinline__ void fft_regs_half(double2 (&v)[16], int u, int c, double* __restrict__ xb,
-                                              const double2* __restrict__ t1, const double2* __restrict__ t2) {
+// Same with an exchange buffer of 8-byte words (half the size): real and imaginary parts go through it one after the
+// other (twice the barriers, same traffic).
+template <int LOGN, class Addr, class Sync = CtaSync>
+__device__ __forceinline__ void fft_regs_half(double2 (&v)[16], int u, const Addr& at, double* __restrict__ xb,
+                                              const double2* __restrict__ t1, const double2* __restrict__ t2,
+                                              const Sync& sync = Sync()) {
     using P = RegPlan<LOGN>;
     using O = Owner<LOGN>;
     dft16(v);
     twiddle1<LOGN>(v, u, t1);
 #pragma unroll
-    for (int q = 0; q < 16; ++q) xb[phi(O::x1_write(u, q)) * C + c] = v[q].x;
-    __syncthreads();
+    for (int q = 0; q < 16; ++q) xb[at(O::x1_write(u, q))] = v[q].x;
+    sync();
 #pragma unroll
-    for (int m = 0; m < 16; ++m) v[m].x = xb[phi(O::x1_read(u, m)) * C + c];  // v[].y still holds pass-1 ownership
-    __syncthreads();
+    for (int m = 0; m < 16; ++m) v[m].x = xb[at(O::x1_read(u, m))];  // v[].y still holds pass-1 ownership
+    sync();
 #pragma unroll
-    for (int q = 0; q < 16; ++q) xb[phi(O::x1_write(u, q)) * C + c] = v[q].y;
-    __syncthreads();
+    for (int q = 0; q < 16; ++q) xb[at(O::x1_write(u, q))] = v[q].y;
+    sync();
 #pragma unroll
-    for (int m = 0; m < 16; ++m) v[m].y = xb[phi(O::x1_read(u, m)) * C + c];
+    for (int m = 0; m < 16; ++m) v[m].y = xb[at(O::x1_read(u, m))];
     dft16(v);
     if constexpr (P::M2 > 1) {
         twiddle2<LOGN>(v, u, t2);
 #pragma unroll
-        for (int q = 0; q < 16; ++q) xb[phi(O::x2_write(u, q)) * C + c] = v[q].x;  // own slots of the last read
-        __syncthreads();
+        for (int q = 0; q < 16; ++q) xb[at(O::x2_write(u, q))] = v[q].x;  // own slots of the last read
+        sync();
 #pragma unroll
-        for (int r = 0; r < 16; ++r) v[r].x = xb[phi(O::x2_read(u, r)) * C + c];  // v[].y still holds pass-2 ownership
-        __syncthreads();
+        for (int r = 0; r < 16; ++r) v[r].x = xb[at(O::x2_read(u, r))];  // v[].y still holds pass-2 ownership
+        sync();
 #pragma unroll
-        for (int q = 0; q < 16; ++q) xb[phi(O::x2_write(u, q)) * C + c] = v[q].y;
-        __syncthreads();
+        for (int q = 0; q < 16; ++q) xb[at(O::x2_write(u, q))] = v[q].y;
+        sync();
 #pragma unroll
-        for (int r = 0; r < 16; ++r) v[r].y = xb[phi(O::x2_read(u, r)) * C + c];
+        for (int r = 0; r < 16; ++r) v[r].y = xb[at(O::x2_read(u, r))];
         dft_groups<P::M2>(v);
+    }
+}
+
+// Two-for-one split after the transform of z = a + i b (a, b real lines): the thread gives up its outputs
+// (frequency out_freq(u, r)) and receives Z[k] and Z[N - k] for k = u + M1 m, m < 8, i.e. k < N/2; on return
+// e[m] = A^[k] = (Z[k] + conj Z[N-k]) / 2 and o[m] = B^[k] = (Z[k] - conj Z[N-k]) / (2i).  8-byte exchange words.
+template <int LOGN, class Addr, class Sync = CtaSync>
+__device__ __forceinline__ void split_two_for_one(double2 (&v)[16], int u, const Addr& at, double* __restrict__ xb,
+                                                  double2 (&e)[8], double2 (&o)[8], const Sync& sync = Sync()) {
+    using P = RegPlan<LOGN>;
+    using O = Owner<LOGN>;
+    sync();  // the last reads of the transform's exchange are complete
+#pragma unroll
+    for (int r = 0; r < 16; ++r) xb[at(O::out_freq(u, r))] = v[r].x;
+    sync();
+    double are[8], bre[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        const int k = u + P::M1 * m;
+        are[m] = xb[at(k)];
+        bre[m] = xb[at((P::N - k) & (P::N - 1))];
+    }
+    sync();
+#pragma unroll
+    for (int r = 0; r < 16; ++r) xb[at(O::out_freq(u, r))] = v[r].y;
+    sync();
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        const int k = u + P::M1 * m;
+        const double aim = xb[at(k)], bim = xb[at((P::N - k) & (P::N - 1))];
+        e[m] = make_double2(0.5 * (are[m] + bre[m]), 0.5 * (aim - bim));
+        o[m] = make_double2(0.5 * (aim + bim), 0.5 * (bre[m] - are[m]));
     }
 }
 

@@ -316,28 +316,15 @@ int fava_fractal_tiles(fava_ctx* ctx, const void* d_field, int dtype, int64_t nz
     FAVA_REQUIRE(cty <= 65535 && tz1 - tz0 <= 65535, "fava_fractal_tiles: grid too large");
     dim3 grid((unsigned)ctx_, (unsigned)cty, (unsigned)(tz1 - tz0));
     cudaStream_t st = (cudaStream_t)stream;
-    // CTA shape: the kernel is bound by its per-row instruction stream, not by occupancy — 512x2, 512x3, 256x4 and
-    // 256x6 (threads x CTAs/SM) measure within 15 % of each other on B200 (profiles/r01_uniform_analysis_kernels.json);
-    // 256x4 is the default, FAVA_FRACTAL_CTA selects another one for tuning.
-    const char* shape = getenv("FAVA_FRACTAL_CTA");
-    const int which = !shape ? 2 : !strcmp(shape, "512x2") ? 0 : !strcmp(shape, "512x3") ? 1 : !strcmp(shape, "256x6") ? 3 : 2;
-#define FAVA_FRACTAL_LAUNCH(T, TH, MC)                                                                       \
-    k_fractal_tiles<T, TH, MC><<<grid, TH, 0, st>>>((const T*)d_field, nz, ny, nx, zf0, tz0, contour,          \
-                                                    (unsigned long long*)d_counts, d_coarse)
-#define FAVA_FRACTAL_DISPATCH(T)                                \
-    switch (which) {                                            \
-        case 0: FAVA_FRACTAL_LAUNCH(T, 512, 2); break;          \
-        case 1: FAVA_FRACTAL_LAUNCH(T, 512, 3); break;          \
-        case 2: FAVA_FRACTAL_LAUNCH(T, 256, 4); break;          \
-        default: FAVA_FRACTAL_LAUNCH(T, 256, 6); break;         \
-    }
-    if (dtype == FAVA_F64) {
-        FAVA_FRACTAL_DISPATCH(double)
-    } else {
-        FAVA_FRACTAL_DISPATCH(float)
-    }
-#undef FAVA_FRACTAL_DISPATCH
-#undef FAVA_FRACTAL_LAUNCH
+    // CTA shape: the kernel is bound by its per-row instruction stream, not by occupancy - 512x2, 512x3, 256x4 and
+    // 256x6 (threads x CTAs/SM) measured within 15 % of each other on B200 (profiles/r01_uniform_analysis_kernels.json);
+    // 256x4 was the fastest and is the one that is built.
+    if (dtype == FAVA_F64)
+        k_fractal_tiles<double, 256, 4><<<grid, 256, 0, st>>>((const double*)d_field, nz, ny, nx, zf0, tz0, contour,
+                                                               (unsigned long long*)d_counts, d_coarse);
+    else
+        k_fractal_tiles<float, 256, 4><<<grid, 256, 0, st>>>((const float*)d_field, nz, ny, nx, zf0, tz0, contour,
+                                                              (unsigned long long*)d_counts, d_coarse);
     FAVA_LAUNCHED();
     return FAVA_OK;
 }

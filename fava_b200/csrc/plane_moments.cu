@@ -76,30 +76,11 @@ __device__ __forceinline__ void load4(const T* rho, const T* ux, const T* uy, co
 // ---- axis 0 (x, the fastest index): column sums -----------------------------------------------
 // A warp owns a 32*V-column strip, a CTA's 8 warps take 8 consecutive rows per step; every thread
 // keeps 13*V accumulators for its V columns.  grid = (column strips, row chunks).
-// WEIGHT (V = 2 only): the pass also writes K4's output w_c = sqrt(rho) u_c for the three components into the
-// row-padded buffers of the spectrum's in-place transform (csrc/spectrum.cu) — the values are in registers anyway,
-// so the spectrum's separate 32 B/cell read of rho,ux,uy,uz disappears.
-struct WeightOut {
-    double* w[3];
-    int64_t pitch;  // doubles per output row
-};
-
-template <int V>
-__device__ __forceinline__ void store_weighted(const WeightOut& wo, int64_t row, int64_t x0, const double (&vr)[V],
-                                               const double (&vx)[V], const double (&vy)[V], const double (&vz)[V]) {
-    static_assert(V == 2, "the fused weighting writes 16-byte pairs");
-    const double s0 = sqrt(vr[0]), s1 = sqrt(vr[1]);
-    const int64_t o = row * wo.pitch + x0;
-    __stcs(reinterpret_cast<double2*>(wo.w[0] + o), make_double2(s0 * vx[0], s1 * vx[1]));
-    __stcs(reinterpret_cast<double2*>(wo.w[1] + o), make_double2(s0 * vy[0], s1 * vy[1]));
-    __stcs(reinterpret_cast<double2*>(wo.w[2] + o), make_double2(s0 * vz[0], s1 * vz[1]));
-}
-
-template <typename T, int V, int U, int NM, bool WEIGHT = false>
+template <typename T, int V, int U, int NM>
 __global__ void __launch_bounds__(kThreads, 2)
     k_moments_cols(const T* __restrict__ rho, const T* __restrict__ ux, const T* __restrict__ uy,
                    const T* __restrict__ uz, int64_t nrows, int64_t nx, const double* __restrict__ piv,
-                   double* __restrict__ partial, int64_t rows_per_chunk, WeightOut wo = WeightOut()) {
+                   double* __restrict__ partial, int64_t rows_per_chunk) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t x0 = ((int64_t)blockIdx.x * 32 + lane) * V;
     const bool active = x0 < nx;
@@ -127,7 +108,6 @@ __global__ void __launch_bounds__(kThreads, 2)
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                if constexpr (WEIGHT) store_weighted<V>(wo, r + (int64_t)u * kWarps, x0, vr[u], vx[u], vy[u], vz[u]);
 #pragma unroll
                 for (int v = 0; v < V; ++v)
                     acc[v].add(vr[u][v], vx[u][v], vy[u][v], vz[u][v], c[0][v], c[1][v], c[2][v]);
@@ -137,7 +117,6 @@ __global__ void __launch_bounds__(kThreads, 2)
             double vr[V], vx[V], vy[V], vz[V];
             const int64_t off = r * nx + x0;
             load4<T, V, NM>(rho, ux, uy, uz, off, vr, vx, vy, vz);
-            if constexpr (WEIGHT) store_weighted<V>(wo, r, x0, vr, vx, vy, vz);
 #pragma unroll
             for (int v = 0; v < V; ++v) acc[v].add(vr[v], vx[v], vy[v], vz[v], c[0][v], c[1][v], c[2][v]);
         }
@@ -436,22 +415,14 @@ static int launch_dense(fava_ctx* ctx, const T* rho, const T* ux, const T* uy, c
 template <typename T, int V, int U>
 static int launch_xz(fava_ctx* ctx, const T* rho, const T* ux, const T* uy, const T* uz, int64_t nz, int64_t ny,
                      int64_t nx, const double* piv_x, const double* piv_z, double* mom_x, double* mom_z,
-                     cudaStream_t st, const WeightOut* wo = nullptr) {
+                     cudaStream_t st) {
     const int64_t strips = ceil_div(nx, 32 * V);
     void* ws;
     int rc = ctx_workspace(ctx, WS_PARTIALS, sizeof(double) * (size_t)nz * kNM * nx, &ws);
     if (rc) return rc;
     double* partial = (double*)ws;
     dim3 grid((unsigned)strips, (unsigned)nz);  // one chunk of ny rows per z-plane
-    if constexpr (V == 2) {
-        if (wo)  // two rows in flight: with U rows the sqrt / store temporaries of the weighting spill at 128 registers
-            k_moments_cols<T, V, 2, kNM, true><<<grid, kThreads, 0, st>>>(rho, ux, uy, uz, nz * ny, nx, piv_x, partial, ny,
-                                                                          *wo);
-        else
-            k_moments_cols<T, V, U, kNM><<<grid, kThreads, 0, st>>>(rho, ux, uy, uz, nz * ny, nx, piv_x, partial, ny);
-    } else {
-        k_moments_cols<T, V, U, kNM><<<grid, kThreads, 0, st>>>(rho, ux, uy, uz, nz * ny, nx, piv_x, partial, ny);
-    }
+    k_moments_cols<T, V, U, kNM><<<grid, kThreads, 0, st>>>(rho, ux, uy, uz, nz * ny, nx, piv_x, partial, ny);
     FAVA_LAUNCHED();
     const int64_t n = (int64_t)FAVA_NMOM * nx;
     k_reduce_partials<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(partial, (int)nz, nx, kNM, FAVA_NMOM, mom_x, 0,
@@ -466,14 +437,13 @@ static int launch_xz(fava_ctx* ctx, const T* rho, const T* ux, const T* uy, cons
 template <typename T, int U>
 static int dispatch_xz(fava_ctx* ctx, const void* rho, const void* ux, const void* uy, const void* uz, int64_t nz,
                        int64_t ny, int64_t nx, const double* piv_x, const double* piv_z, double* mom_x,
-                       double* mom_z, cudaStream_t st, const WeightOut* wo = nullptr) {
+                       double* mom_z, cudaStream_t st) {
     const size_t va = 2 * sizeof(T);
     const bool vec = (nx % 2 == 0) && aligned_to(rho, va) && aligned_to(ux, va) && aligned_to(uy, va) &&
                      aligned_to(uz, va);
-    if (wo && !vec) return set_error(FAVA_EINVAL, "fused weighting needs an even nx and 16-byte aligned fields");
     if (vec)
         return launch_xz<T, 2, U>(ctx, (const T*)rho, (const T*)ux, (const T*)uy, (const T*)uz, nz, ny, nx, piv_x,
-                                  piv_z, mom_x, mom_z, st, wo);
+                                  piv_z, mom_x, mom_z, st);
     return launch_xz<T, 1, U>(ctx, (const T*)rho, (const T*)ux, (const T*)uy, (const T*)uz, nz, ny, nx, piv_x, piv_z,
                               mom_x, mom_z, st);
 }
@@ -551,27 +521,6 @@ int fava_plane_moments_xz(fava_ctx* ctx, const void* d_rho, const void* d_ux, co
     if (dtype == FAVA_F64)
         return dispatch_xz<double, 4>(ctx, d_rho, d_ux, d_uy, d_uz, nz, ny, nx, d_piv_x, d_piv_z, d_mom_x, d_mom_z, st);
     return dispatch_xz<float, 8>(ctx, d_rho, d_ux, d_uy, d_uz, nz, ny, nx, d_piv_x, d_piv_z, d_mom_x, d_mom_z, st);
-}
-
-int fava_plane_moments_xz_weight3(fava_ctx* ctx, const void* d_rho, const void* d_ux, const void* d_uy,
-                                  const void* d_uz, int dtype, int64_t nz, int64_t ny, int64_t nx,
-                                  const double* d_piv_x, const double* d_piv_z, double* d_mom_x, double* d_mom_z,
-                                  int64_t pitch, double* d_wx, double* d_wy, double* d_wz, void* stream) {
-    FAVA_REQUIRE(ctx && d_rho && d_ux && d_uy && d_uz && d_piv_x && d_piv_z && d_mom_x && d_mom_z && d_wx && d_wy && d_wz,
-                 "fava_plane_moments_xz_weight3: NULL argument");
-    FAVA_REQUIRE(nz > 0 && ny > 0 && nx > 0 && nz <= 65535, "fava_plane_moments_xz_weight3: bad shape %lldx%lldx%lld",
-                 (long long)nz, (long long)ny, (long long)nx);
-    FAVA_REQUIRE(pitch >= nx && (pitch & 1) == 0 && aligned_to(d_wx, 16) && aligned_to(d_wy, 16) && aligned_to(d_wz, 16),
-                 "fava_plane_moments_xz_weight3: pitch must be even and >= nx, outputs 16-byte aligned");
-    FAVA_REQUIRE(dtype == FAVA_F32 || dtype == FAVA_F64, "fava_plane_moments_xz_weight3: bad dtype %d", dtype);
-    DeviceGuard g(ctx->device);
-    cudaStream_t st = (cudaStream_t)stream;
-    WeightOut wo;
-    wo.w[0] = d_wx, wo.w[1] = d_wy, wo.w[2] = d_wz;
-    wo.pitch = pitch;
-    if (dtype == FAVA_F64)
-        return dispatch_xz<double, 4>(ctx, d_rho, d_ux, d_uy, d_uz, nz, ny, nx, d_piv_x, d_piv_z, d_mom_x, d_mom_z, st, &wo);
-    return dispatch_xz<float, 8>(ctx, d_rho, d_ux, d_uy, d_uz, nz, ny, nx, d_piv_x, d_piv_z, d_mom_x, d_mom_z, st, &wo);
 }
 
 int fava_plane_sum(fava_ctx* ctx, const void* d_field, int dtype, int64_t nz, int64_t ny, int64_t nx, int axis,

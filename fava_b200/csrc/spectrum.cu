@@ -3,11 +3,12 @@
 // thread, a 3*N^3 fp64 k-grid, fftshift copies and three scipy binned_statistic passes).
 //
 // Pipeline (per GPU; every array stays in FILE order [z][y][x], x fastest):
-//   K4  k_ke_weight3   w_n = sqrt(rho) * u_n for the three components in ONE pass over rho,ux,uy,uz,
-//                      written into the row-padded layout an in-place real-to-complex FFT needs.
-//   lib cuFFT          the 3-D FFT — the ONLY library call on this path (BASELINE.json north_star):
-//                      batched 2-D D2Z over (y,x) per z-plane, then strided 1-D Z2Z along z, both in
-//                      place.  Hermitian (r2c) storage: complex [kz][ky][kx = 0..N/2].
+//   transform          power-of-two N (256..2048): the hand-written passes of csrc/fft.cu - weighting fused into the
+//                      x pass, pruned y and z passes - in Hermitian storage complex [kz][ky][kx = 0..N/2-1]
+//                      (row pitch N/2: the Nyquist column is never read by a bin and is not stored).
+//                      Any other even N:  K4 k_ke_weight3 (w_n = sqrt(rho) u_n, one pass, row-padded) + cuFFT -
+//                      the only library call on this path (BASELINE.json north_star) - batched 2-D D2Z over
+//                      (y,x), then strided 1-D Z2Z along z, in place; row pitch N/2+1.
 //   K6  k_spectrum_bin |u^|^2, the reference's longitudinal projection INCLUDING its `.T` quirk
 //                      (FlashUniform.py:281: ffts[n].T reverses all axes, i.e. the operand is taken at
 //                      the transposed wavevector (kz,ky,kx)), shell index floor(|k|+1/2) in exact
@@ -69,9 +70,9 @@ constexpr int kBinWarps = kBinT / 32;
 constexpr int kSlots = 64;     // shell span of one tile (<= 31*sqrt(2) + 2)
 
 struct BinParams {
-    int n, nxh, ny_local, nbins, kmax2, npairs;
+    int n, pitch, ny_local, nbins, kmax2, npairs;  // pitch = complex elements per kx row (N/2 or N/2+1)
     int64_t ngroups;
-    int64_t zstride;  // ny_local * nxh (complex elements per kz plane)
+    int64_t zstride;  // ny_local * pitch (complex elements per kz plane)
     const int32_t* ky_of_local;  // NULL = identity (local row jl holds global ky index jl)
     const int32_t* local_of_ky;  // NULL = identity
     double norm2;
@@ -145,8 +146,8 @@ __global__ void __launch_bounds__(kBinT, 2)
                 const int kxa = a0 + ia;
                 const bool ok = qok && kxa < nh;
                 int64_t off = 0;
-                if (ok) off = T.neg ? (int64_t)((n - kxa) % n) * p.zstride + (int64_t)T.jml * p.nxh + q
-                                    : (int64_t)kxa * p.zstride + (int64_t)T.jl * p.nxh + q;
+                if (ok) off = T.neg ? (int64_t)((n - kxa) % n) * p.zstride + (int64_t)T.jml * p.pitch + q
+                                    : (int64_t)kxa * p.zstride + (int64_t)T.jl * p.pitch + q;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) cp_async16(&S[c][ia][lane], F[c] + off, ok);
             }
@@ -162,7 +163,7 @@ __global__ void __launch_bounds__(kBinT, 2)
                 const int q = b0 + warp + kBinWarps * i;
                 const bool ok = kx < nh && q < nh && !(T.neg && q == 0);
                 const int l = T.neg ? n - q : q;
-                const int64_t off = ok ? (int64_t)l * p.zstride + (int64_t)T.jl * p.nxh + kx : 0;
+                const int64_t off = ok ? (int64_t)l * p.zstride + (int64_t)T.jl * p.pitch + kx : 0;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) d[c][i] = ok ? __ldcs(F[c] + off) : make_double2(0.0, 0.0);
             }
@@ -380,56 +381,41 @@ int fava_ke_weight3(fava_ctx* ctx, const void* d_rho, const void* d_ux, const vo
     return FAVA_OK;
 }
 
-int fava_fft_xy(fava_ctx* ctx, double* d_data, int64_t nz_local, int64_t ny, int64_t nx, void* stream) {
-    FAVA_REQUIRE(ctx && d_data, "fava_fft_xy: NULL argument");
-    FAVA_REQUIRE(nz_local > 0 && ny > 0 && nx > 1 && (nx & 1) == 0, "fava_fft_xy: bad shape");
-    DeviceGuard g(ctx->device);
-    return exec_plan(ctx, PLAN_XY, nz_local, ny, nx, d_data, (cudaStream_t)stream);
-}
+int64_t fava_spectral_pitch(int64_t n) { return fft_native_supported(n) ? n / 2 : n / 2 + 1; }
 
-int fava_fft_z(fava_ctx* ctx, double* d_data, int64_t nz, int64_t rows, void* stream) {
-    FAVA_REQUIRE(ctx && d_data, "fava_fft_z: NULL argument");
-    FAVA_REQUIRE(nz > 0 && rows > 0, "fava_fft_z: bad shape");
-    DeviceGuard g(ctx->device);
-    return exec_plan(ctx, PLAN_Z, nz, rows, 0, d_data, (cudaStream_t)stream);
-}
-
-int fava_ke_weight_fft_xy(fava_ctx* ctx, const void* d_rho, const void* d_ux, const void* d_uy, const void* d_uz,
-                          int dtype, int64_t nz_local, int64_t n, double* d_wx, double* d_wy, double* d_wz,
-                          void* stream) {
-    FAVA_REQUIRE(ctx && d_rho && d_ux && d_uy && d_uz && d_wx && d_wy && d_wz, "fava_ke_weight_fft_xy: NULL argument");
-    FAVA_REQUIRE(nz_local > 0, "fava_ke_weight_fft_xy: empty slab");
-    FAVA_REQUIRE(dtype == FAVA_F32 || dtype == FAVA_F64, "fava_ke_weight_fft_xy: bad dtype %d", dtype);
-    int rc = check_cube(n, "fava_ke_weight_fft_xy");
+int fava_ke_transform_x(fava_ctx* ctx, const void* d_rho, const void* d_ux, const void* d_uy, const void* d_uz, int dtype,
+                        int64_t nz_local, int64_t n, double* d_wx, double* d_wy, double* d_wz, void* stream) {
+    FAVA_REQUIRE(ctx && d_rho && d_ux && d_uy && d_uz && d_wx && d_wy && d_wz, "fava_ke_transform_x: NULL argument");
+    FAVA_REQUIRE(nz_local > 0, "fava_ke_transform_x: empty slab");
+    FAVA_REQUIRE(dtype == FAVA_F32 || dtype == FAVA_F64, "fava_ke_transform_x: bad dtype %d", dtype);
+    int rc = check_cube(n, "fava_ke_transform_x");
     if (rc) return rc;
-    // Optional plane groups (FAVA_XY_GROUP = z-planes per group): K4 and the two sub-passes of the 2-D transform
-    // run back to back on a few planes at a time, hoping to keep the weighted planes in the 126 MB L2.  Measured on
-    // B200 at 1024^3 (CUDA-graph replay, so no launch overhead): whole slab 38.1 ms, groups of 8 / 4 / 2 / 1 planes
-    // 37.5 / 38.8 / 42.8 / 62.0 ms - the small launches lose more than the L2 gives back, so the default is the
-    // whole slab in one go.
-    const int64_t nxh = n / 2 + 1;
-    int64_t group = nz_local;
-    if (const char* e = getenv("FAVA_XY_GROUP")) {
-        const long v = atol(e);
-        if (v > 0) group = v;
-    }
-    group = std::min<int64_t>(group, nz_local);
-    const size_t esz = dtype == FAVA_F64 ? 8 : 4;
-    double* w[3] = {d_wx, d_wy, d_wz};
-    for (int64_t z0 = 0; z0 < nz_local; z0 += group) {
-        const int64_t g = std::min<int64_t>(group, nz_local - z0);
-        const size_t in_off = (size_t)z0 * n * n * esz;
-        const size_t out_off = (size_t)z0 * n * 2 * nxh;  // doubles
-        rc = fava_ke_weight3(ctx, (const char*)d_rho + in_off, (const char*)d_ux + in_off, (const char*)d_uy + in_off,
-                             (const char*)d_uz + in_off, dtype, g * n, n, 2 * nxh, d_wx + out_off, d_wy + out_off,
-                             d_wz + out_off, stream);
-        if (rc) return rc;
-        for (int c = 0; c < 3; ++c) {
-            rc = fava_fft_xy(ctx, w[c] + out_off, g, n, n, stream);
-            if (rc) return rc;
-        }
-    }
-    return FAVA_OK;
+    if (fft_native_supported(n))
+        return fava_fft_x_weight3(ctx, d_rho, d_ux, d_uy, d_uz, dtype, nz_local * n, n, n / 2, d_wx, d_wy, d_wz, stream);
+    return fava_ke_weight3(ctx, d_rho, d_ux, d_uy, d_uz, dtype, nz_local * n, n, 2 * (n / 2 + 1), d_wx, d_wy, d_wz, stream);
+}
+
+int fava_ke_transform_y(fava_ctx* ctx, double* d_w, int64_t nz_local, int64_t n, void* stream) {
+    FAVA_REQUIRE(ctx && d_w, "fava_ke_transform_y: NULL argument");
+    FAVA_REQUIRE(nz_local > 0, "fava_ke_transform_y: empty slab");
+    int rc = check_cube(n, "fava_ke_transform_y");
+    if (rc) return rc;
+    if (fft_native_supported(n)) return fava_fft_cols(ctx, d_w, n, n / 2, n / 2, n, nz_local, 1, 1, nullptr, stream);
+    DeviceGuard g(ctx->device);
+    return exec_plan(ctx, PLAN_XY, nz_local, n, n, d_w, (cudaStream_t)stream);
+}
+
+int fava_ke_transform_z(fava_ctx* ctx, double* d_w, int64_t n, int64_t ny_local, const int32_t* d_ky_of_local,
+                        void* stream) {
+    FAVA_REQUIRE(ctx && d_w, "fava_ke_transform_z: NULL argument");
+    FAVA_REQUIRE(ny_local > 0 && ny_local <= n, "fava_ke_transform_z: ny_local %lld not in 1..%lld", (long long)ny_local,
+                 (long long)n);
+    FAVA_REQUIRE(d_ky_of_local || ny_local == n, "fava_ke_transform_z: a partial ky range needs the ky map");
+    int rc = check_cube(n, "fava_ke_transform_z");
+    if (rc) return rc;
+    if (fft_native_supported(n)) return fava_fft_cols(ctx, d_w, n, n / 2, n / 2, ny_local, n, 2, 2, d_ky_of_local, stream);
+    DeviceGuard g(ctx->device);
+    return exec_plan(ctx, PLAN_Z, n, ny_local * (n / 2 + 1), 0, d_w, (cudaStream_t)stream);
 }
 
 int fava_spectrum_bin(fava_ctx* ctx, const double* d_fx, const double* d_fy, const double* d_fz, int64_t n,
@@ -446,7 +432,7 @@ int fava_spectrum_bin(fava_ctx* ctx, const double* d_fx, const double* d_fy, con
     DeviceGuard g(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
     BinParams p;
-    p.n = (int)n, p.nxh = (int)(n / 2 + 1), p.ny_local = (int)ny_local;
+    p.n = (int)n, p.pitch = (int)fava_spectral_pitch(n), p.ny_local = (int)ny_local;
     p.nbins = (int)(n / 2 - 1);
     p.kmax2 = (int)(n * n / 4 - 3 * n / 2 + 2);
     const int nt = (int)((n / 2 + kTS - 1) / kTS);  // 32-wide tiles of kx and of |kz|
@@ -455,7 +441,7 @@ int fava_spectrum_bin(fava_ctx* ctx, const double* d_fx, const double* d_fy, con
     // +-ky symmetric set otherwise (fava_b200/spectrum.py:ky_ownership)
     const int64_t npos = d_ky_of_local ? (ny_local + 1) / 2 : n / 2;
     p.ngroups = npos * p.npairs;
-    p.zstride = ny_local * (int64_t)p.nxh;
+    p.zstride = ny_local * (int64_t)p.pitch;
     p.ky_of_local = d_ky_of_local, p.local_of_ky = d_local_of_ky;
     p.norm2 = norm * norm;
     const size_t nb_pad = (size_t)((3 * p.nbins + 1) & ~1);
@@ -506,8 +492,7 @@ int fava_ke_spectrum(fava_ctx* ctx, const void* d_rho, const void* d_ux, const v
     int rc = check_cube(n, "fava_ke_spectrum");
     if (rc) return rc;
     DeviceGuard g(ctx->device);
-    const int64_t nxh = n / 2 + 1;
-    const size_t comp_bytes = sizeof(double) * 2 * (size_t)(n * n * nxh);
+    const size_t comp_bytes = sizeof(double) * 2 * (size_t)(n * n * fava_spectral_pitch(n));
     void* w[3];
     for (int c = 0; c < 3; ++c) {
         rc = ctx_workspace(ctx, WS_FFT1 + c, comp_bytes, &w[c]);
@@ -516,27 +501,15 @@ int fava_ke_spectrum(fava_ctx* ctx, const void* d_rho, const void* d_ux, const v
     void* sums;
     rc = ctx_workspace(ctx, WS_AUX, sizeof(double) * 3 * (size_t)(n / 2 - 1), &sums);
     if (rc) return rc;
-    if (fft_native_supported(n)) {
-        // hand-written path: weighting fused into the x pass, strided y pass, disc-pruned z pass (csrc/fft.cu)
-        rc = fava_fft_x_weight3(ctx, d_rho, d_ux, d_uy, d_uz, dtype, n * n, n, (double*)w[0], (double*)w[1],
-                                (double*)w[2], stream);
+    rc = fava_ke_transform_x(ctx, d_rho, d_ux, d_uy, d_uz, dtype, n, n, (double*)w[0], (double*)w[1], (double*)w[2], stream);
+    if (rc) return rc;
+    for (int c = 0; c < 3; ++c) {
+        rc = fava_ke_transform_y(ctx, (double*)w[c], n, n, stream);
         if (rc) return rc;
-        for (int c = 0; c < 3; ++c) {
-            rc = fava_fft_cols(ctx, (double*)w[c], n, nxh, n, 0, nullptr, stream);
-            if (rc) return rc;
-        }
-        for (int c = 0; c < 3; ++c) {
-            rc = fava_fft_cols(ctx, (double*)w[c], n, n * nxh, 1, n, nullptr, stream);
-            if (rc) return rc;
-        }
-    } else {
-        rc = fava_ke_weight_fft_xy(ctx, d_rho, d_ux, d_uy, d_uz, dtype, n, n, (double*)w[0], (double*)w[1], (double*)w[2],
-                                   stream);
+    }
+    for (int c = 0; c < 3; ++c) {
+        rc = fava_ke_transform_z(ctx, (double*)w[c], n, n, nullptr, stream);
         if (rc) return rc;
-        for (int c = 0; c < 3; ++c) {
-            rc = fava_fft_z(ctx, (double*)w[c], n, n * nxh, stream);
-            if (rc) return rc;
-        }
     }
     const double norm = 1.0 / ((double)n * (double)n * (double)n);  // norm="forward" (FlashUniform.py:268)
     rc = fava_spectrum_bin(ctx, (const double*)w[0], (const double*)w[1], (const double*)w[2], n, n, nullptr, nullptr,

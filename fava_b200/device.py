@@ -130,25 +130,14 @@ def plane_moments(rho, ux, uy, uz, axis: int, pivots: torch.Tensor | None = None
     return out, pivots
 
 
-def plane_moments_xz(rho, ux, uy, uz, weighted_out=None):
-    """Moments for axis x and axis z from one pass (fava_plane_moments_xz) -> ((mom_x, piv_x), (mom_z, piv_z)).
-    `weighted_out` = three device addresses: the pass also writes sqrt(rho) u_n there in the row-padded layout of the
-    spectrum's in-place transform (fava_plane_moments_xz_weight3)."""
+def plane_moments_xz(rho, ux, uy, uz):
+    """Moments for axis x and axis z from one pass (fava_plane_moments_xz) -> ((mom_x, piv_x), (mom_z, piv_z))."""
     nz, ny, nx = _check_fields(rho, ux, uy, uz)
     ctx = get_context(rho.device)
     piv_x = plane_pivots(ux, uy, uz, 0)
     piv_z = plane_pivots(ux, uy, uz, 2)
     mom_x = torch.empty((FAVA_NMOM, nx), dtype=torch.float64, device=rho.device)
     mom_z = torch.empty((FAVA_NMOM, nz), dtype=torch.float64, device=rho.device)
-    if weighted_out is not None:
-        wx, wy, wz = (C.c_void_p(int(p)) for p in weighted_out)
-        _lib.check(
-            ctx.lib.fava_plane_moments_xz_weight3(ctx.handle, _ptr(rho), _ptr(ux), _ptr(uy), _ptr(uz), _dtype_code(rho),
-                                                  nz, ny, nx, _ptr(piv_x), _ptr(piv_z), _ptr(mom_x), _ptr(mom_z),
-                                                  2 * (nx // 2 + 1), wx, wy, wz, _stream(rho)),
-            "fava_plane_moments_xz_weight3",
-        )
-        return (mom_x, piv_x), (mom_z, piv_z)
     _lib.check(
         ctx.lib.fava_plane_moments_xz(ctx.handle, _ptr(rho), _ptr(ux), _ptr(uy), _ptr(uz), _dtype_code(rho), nz, ny, nx,
                                       _ptr(piv_x), _ptr(piv_z), _ptr(mom_x), _ptr(mom_z), _stream(rho)),
@@ -430,31 +419,65 @@ def _cur_stream(dev) -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
-def ke_weight3(rho, ux, uy, uz, wx: int, wy: int, wz: int) -> None:
+def spectral_pitch(n: int) -> int:
+    """Complex elements per kx row of the spectral buffers (fava_spectral_pitch): n/2 on the hand-written transform
+    path (power-of-two n in [256, 2048]; the Nyquist column is not stored), n/2 + 1 on the cuFFT path."""
+    return int(_lib.load().fava_spectral_pitch(int(n)))
+
+
+def spectral_bytes(n: int, planes: int) -> int:
+    """Bytes of one component's spectral buffer holding `planes` planes of n x pitch complex numbers."""
+    return 16 * int(planes) * int(n) * spectral_pitch(n)
+
+
+def ke_weight3(rho, ux, uy, uz, wx: int, wy: int, wz: int, pitch: int | None = None) -> None:
+    """K4 alone (fava_ke_weight3): sqrt(rho) u_c as real rows of `pitch` doubles (default 2 (nx/2 + 1))."""
     nz, ny, nx = _check_fields(rho, ux, uy, uz)
     ctx = get_context(rho.device)
+    pitch = 2 * (nx // 2 + 1) if pitch is None else int(pitch)
     _lib.check(ctx.lib.fava_ke_weight3(ctx.handle, _ptr(rho), _ptr(ux), _ptr(uy), _ptr(uz), _dtype_code(rho), nz * ny, nx,
-                                       2 * (nx // 2 + 1), C.c_void_p(wx), C.c_void_p(wy), C.c_void_p(wz), _stream(rho)),
+                                       pitch, C.c_void_p(wx), C.c_void_p(wy), C.c_void_p(wz), _stream(rho)),
                "fava_ke_weight3")
 
 
-def ke_weight_fft_xy(rho, ux, uy, uz, wx: int, wy: int, wz: int) -> None:
-    """Weighting + 2-D transform of a slab in L2-resident plane groups (fava_ke_weight_fft_xy)."""
+def ke_transform_x(rho, ux, uy, uz, wx: int, wy: int, wz: int) -> None:
+    """Stage 1 of the transform of a z-slab [nz_local][n][n] (fava_ke_transform_x): weighting fused with the x pass
+    (hand-written path) or the weighting alone (cuFFT path)."""
     nz, ny, nx = _check_fields(rho, ux, uy, uz)
+    if ny != nx:
+        raise ValueError(f"the spectrum needs square planes, got {ny} x {nx}")
     ctx = get_context(rho.device)
-    _lib.check(ctx.lib.fava_ke_weight_fft_xy(ctx.handle, _ptr(rho), _ptr(ux), _ptr(uy), _ptr(uz), _dtype_code(rho), nz, nx,
-                                             C.c_void_p(wx), C.c_void_p(wy), C.c_void_p(wz), _stream(rho)),
-               "fava_ke_weight_fft_xy")
+    _lib.check(ctx.lib.fava_ke_transform_x(ctx.handle, _ptr(rho), _ptr(ux), _ptr(uy), _ptr(uz), _dtype_code(rho), nz, nx,
+                                           C.c_void_p(wx), C.c_void_p(wy), C.c_void_p(wz), _stream(rho)),
+               "fava_ke_transform_x")
 
 
-def fft_xy(data: int, nz_local: int, ny: int, nx: int, dev) -> None:
+def ke_transform_y(w: int, nz_local: int, n: int, dev) -> None:
+    """Stage 2, one component, in place: complex [nz_local][ky][kx] afterwards (fava_ke_transform_y)."""
     ctx = get_context(dev)
-    _lib.check(ctx.lib.fava_fft_xy(ctx.handle, C.c_void_p(data), nz_local, ny, nx, _cur_stream(dev)), "fava_fft_xy")
+    _lib.check(ctx.lib.fava_ke_transform_y(ctx.handle, C.c_void_p(w), int(nz_local), int(n), _cur_stream(dev)),
+               "fava_ke_transform_y")
 
 
-def fft_z(data: int, nz: int, rows: int, dev) -> None:
+def ke_transform_z(w: int, n: int, ny_local: int, ky_of_local, dev) -> None:
+    """Stage 3, one component, in place: transform along z of complex [n][ny_local][pitch] (fava_ke_transform_z)."""
     ctx = get_context(dev)
-    _lib.check(ctx.lib.fava_fft_z(ctx.handle, C.c_void_p(data), nz, rows, _cur_stream(dev)), "fava_fft_z")
+    _lib.check(ctx.lib.fava_ke_transform_z(ctx.handle, C.c_void_p(w), int(n), int(ny_local), _ptr(ky_of_local),
+                                           _cur_stream(dev)), "fava_ke_transform_z")
+
+
+def ke_transform_xy(rho, ux, uy, uz, wx: int, wy: int, wz: int) -> None:
+    """Stages 1 + 2 of a slab (or of a chunk of planes of it) for the three components."""
+    nz, _, n = (int(v) for v in rho.shape)
+    ke_transform_x(rho, ux, uy, uz, wx, wy, wz)
+    for w in (wx, wy, wz):
+        ke_transform_y(w, nz, n, rho.device)
+
+
+def reserve_sms(nsm: int, dev=None) -> None:
+    """Persistent transform kernels leave `nsm` SMs to a concurrent exchange kernel (fava_reserve_sms)."""
+    ctx = get_context(dev)
+    _lib.check(ctx.lib.fava_reserve_sms(ctx.handle, int(nsm)), "fava_reserve_sms")
 
 
 def a2a_pack(src: int, peer_table: torch.Tensor, ky_of_dest: torch.Tensor, rank: int, world: int, nz_local: int, n: int,
@@ -462,15 +485,6 @@ def a2a_pack(src: int, peer_table: torch.Tensor, ky_of_dest: torch.Tensor, rank:
     ctx = get_context(peer_table.device)
     _lib.check(ctx.lib.fava_a2a_pack(ctx.handle, C.c_void_p(src), _ptr(peer_table), _ptr(ky_of_dest), rank, world,
                                      nz_local, n, nyl, _stream(peer_table)), "fava_a2a_pack")
-
-
-def a2a_copy(src: int, peer_ptrs: np.ndarray, ky_of_dest: np.ndarray, rank: int, world: int, nz_local: int, n: int,
-             nyl: int, dev) -> None:
-    """Copy-engine form of the exchange (fava_a2a_copy); peer_ptrs uint64[world], ky_of_dest int32[world][nyl] on the host."""
-    ctx = get_context(dev)
-    _lib.check(ctx.lib.fava_a2a_copy(ctx.handle, C.c_void_p(src), C.c_void_p(peer_ptrs.ctypes.data),
-                                     C.c_void_p(ky_of_dest.ctypes.data), rank, world, nz_local, n, nyl, _cur_stream(dev)),
-               "fava_a2a_copy")
 
 
 def spectrum_bin(fx: int, fy: int, fz: int, n: int, ny_local: int, ky_of_local, local_of_ky, sums: torch.Tensor) -> None:
@@ -494,17 +508,19 @@ def fft_native_supported(n: int) -> bool:
     return bool(_lib.load().fava_fft_native_supported(int(n)))
 
 
-def fft_x_weight3(rho, ux, uy, uz, fx: int, fy: int, fz: int) -> None:
-    """x pass fused with the weighting (fava_fft_x_weight3): out complex [nz*ny][nx/2+1] per component."""
+def fft_x_weight3(rho, ux, uy, uz, fx: int, fy: int, fz: int, pitch: int | None = None) -> None:
+    """x pass fused with the weighting (fava_fft_x_weight3): kx = 0..nx/2-1 into complex rows of `pitch` elements."""
     nz, ny, nx = _check_fields(rho, ux, uy, uz)
     ctx = get_context(rho.device)
+    pitch = nx // 2 if pitch is None else int(pitch)
     _lib.check(ctx.lib.fava_fft_x_weight3(ctx.handle, _ptr(rho), _ptr(ux), _ptr(uy), _ptr(uz), _dtype_code(rho), nz * ny, nx,
-                                          C.c_void_p(fx), C.c_void_p(fy), C.c_void_p(fz), _stream(rho)),
+                                          pitch, C.c_void_p(fx), C.c_void_p(fy), C.c_void_p(fz), _stream(rho)),
                "fava_fft_x_weight3")
 
 
-def fft_cols(data: int, n: int, ncols: int, nbatch: int, dev, prune_grid_n: int = 0, ky_of_local=None) -> None:
-    """In-place strided column FFT (fava_fft_cols) of complex [nbatch][n][ncols]."""
+def fft_cols(data: int, n: int, pitch: int, ncols: int, d1: int, d2: int, line_dim: int, dev, prune_mode: int = 0,
+             ky_of_batch=None) -> None:
+    """In-place FFT of length n along dimension `line_dim` of complex [d2][d1][pitch] (fava_fft_cols)."""
     ctx = get_context(dev)
-    _lib.check(ctx.lib.fava_fft_cols(ctx.handle, C.c_void_p(data), n, ncols, nbatch, int(prune_grid_n),
-                                     _ptr(ky_of_local), _cur_stream(dev)), "fava_fft_cols")
+    _lib.check(ctx.lib.fava_fft_cols(ctx.handle, C.c_void_p(data), int(n), int(pitch), int(ncols), int(d1), int(d2),
+                                     int(line_dim), int(prune_mode), _ptr(ky_of_batch), _cur_stream(dev)), "fava_fft_cols")

@@ -48,6 +48,21 @@ def init_from_env(backend: str | None = None) -> tuple[int, int, int]:
     return rank(), world_size(), local
 
 
+def bind_to_gpu_numa(local_gpu: int) -> bool:
+    """Pin this process to the CPUs next to its GPU (NVML's ideal affinity), so that pinned staging buffers allocated
+    afterwards live on the GPU's NUMA node and the H2D copies of several ranks do not cross the socket link.
+    Best effort: returns False when NVML is not importable or refuses."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(int(local_gpu))
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        return True
+    except Exception:
+        return False
+
+
 def parallel_range(iterations: int, r: int | None = None, p: int | None = None) -> tuple[int, int]:
     """Contiguous block split with the remainder on the low ranks (fava/util/_mpi.py:68-77 and
     _flash.py:166-187 use the same rule)."""
@@ -82,12 +97,24 @@ def broadcast_(t: torch.Tensor, src: int = 0) -> torch.Tensor:
 
 
 def all_gather_cat(t: torch.Tensor, dim: int = 0) -> torch.Tensor:
-    """Concatenate equally-shaped per-rank tensors along `dim` (rank order)."""
+    """Concatenate the per-rank tensors along `dim` in rank order.  The parts may differ in length along `dim`
+    (z-slabs of a grid whose height is not a multiple of the rank count, `parallel_range`): lengths are exchanged
+    first and the parts padded to the longest for the collective."""
     if world_size() == 1:
         return t
-    parts = [torch.empty_like(t) for _ in range(world_size())]
-    dist.all_gather(parts, t.contiguous())
-    return torch.cat(parts, dim=dim)
+    n = torch.tensor([t.shape[dim]], dtype=torch.int64, device=t.device)
+    counts = [torch.zeros_like(n) for _ in range(world_size())]
+    dist.all_gather(counts, n)
+    counts = [int(c.item()) for c in counts]
+    longest = max(counts)
+    src = t.contiguous()
+    if t.shape[dim] < longest:
+        pad_shape = list(t.shape)
+        pad_shape[dim] = longest - t.shape[dim]
+        src = torch.cat([src, torch.zeros(pad_shape, dtype=t.dtype, device=t.device)], dim=dim).contiguous()
+    parts = [torch.empty_like(src) for _ in range(world_size())]
+    dist.all_gather(parts, src)
+    return torch.cat([p.narrow(dim, 0, c) for p, c in zip(parts, counts)], dim=dim)
 
 
 def barrier() -> None:

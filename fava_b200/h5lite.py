@@ -20,11 +20,14 @@ III.B symbol-table nodes, III.D local heaps, IV.A object headers and messages 0x
 
 from __future__ import annotations
 
+import logging
 import os
 import struct
 from pathlib import Path
 
 import numpy as np
+
+logger = logging.getLogger(__name__)
 
 SIGNATURE = b"\x89HDF\r\n\x1a\n"
 UNDEF = 0xFFFFFFFFFFFFFFFF
@@ -555,7 +558,19 @@ class _Writer:
             pos += nb
         eof = pos
 
-        with open(self.path, "wb") as f:
+        # write next to the target and rename over it: a crash, an OOM kill or ENOSPC in the middle of a flush must
+        # not destroy results that are already on disk (mode "a" re-writes the whole file, and the pipeline caches
+        # its per-file results there; h5py's append never re-writes existing objects)
+        tmp = self.path.with_name(f".{self.path.name}.tmp{os.getpid()}")
+        try:
+            self._write_file(tmp, plans, datasets, data_addr, root_lay, eof, btree_bytes, per)
+            os.replace(tmp, self.path)
+        finally:
+            if tmp.exists():
+                tmp.unlink()
+
+    def _write_file(self, target, plans, datasets, data_addr, root_lay, eof, btree_bytes, per) -> None:
+        with open(target, "wb") as f:
             sb = SIGNATURE + struct.pack("<BBBBBBBBHHI", 0, 0, 0, 0, 0, 8, 8, 0, self.LEAF_K, self.INTERNAL_K, 0)
             sb += struct.pack("<4Q", 0, UNDEF, eof, UNDEF)
             sb += struct.pack("<QQII2Q", 0, root_lay["ohdr"], 1, 0, root_lay["btree"], root_lay["heap_addr"])
@@ -601,6 +616,8 @@ class _Writer:
                 plain = flat.dtype.fields is None and flat.dtype.kind != "S" and flat.ndim > 0
                 f.write(memoryview(flat).cast("B") if plain else flat.tobytes())
             f.truncate(eof)
+            f.flush()
+            os.fsync(f.fileno())
 
 
 def _load_tree(group: "Group", out: WGroup) -> WGroup:
@@ -635,9 +652,15 @@ class File:
         elif mode in ("a", "r+"):
             tree = WGroup()
             if Path(name).is_file() and Path(name).stat().st_size > 0:
-                self._reader = _Reader(Path(name))
-                _load_tree(self._read_root(), tree)
-                self._reader.close()
+                try:
+                    self._reader = _Reader(Path(name))
+                    _load_tree(self._read_root(), tree)
+                    self._reader.close()
+                except Exception as exc:  # a truncated / foreign file: start over instead of blocking every later run
+                    logger.warning("h5lite: %s is unreadable (%s); starting from an empty file", name, exc)
+                    if self._reader is not None:
+                        self._reader.close()
+                    tree = WGroup()
                 self._reader = None
             elif mode == "r+":
                 raise FileNotFoundError(name)

@@ -1,17 +1,16 @@
 """Slab-decomposed kinetic-energy spectrum (BASELINE configs[3]: 1024^3 at 1/2/4/8 B200).
 
-Rank r holds z-planes [r*nzl, (r+1)*nzl) of rho, ux, uy, uz.  Per velocity component:
-  weight (K4) -> in-place 2-D FFT over (y,x) of the local planes (cuFFT D2Z) -> slab->pencil exchange
-  (K5: ONE kernel gathers the ky rows each destination owns and stores them straight into that rank's
-  receive buffer over NVLink peer mappings) -> 1-D FFT along z (cuFFT Z2Z) -> shell binning (K6) ->
-  one all-reduce of the [3][N/2-1] shell sums.
+Rank r holds z-planes [r*nzl, (r+1)*nzl) of rho, ux, uy, uz.
+  stage 1: weighting fused with the x transform of the local planes, all three components in one pass;
+  per component: stage 2 (y transform, in place) -> slab->pencil exchange (K5: ONE kernel gathers the ky rows each
+  destination owns and stores them straight into that rank's receive buffer over NVLink peer mappings) ->
+  stage 3 (z transform, pruned to the spectral sphere) ; then shell binning (K6) and one all-reduce of the
+  [3][N/2-1] shell sums.  (Grid sizes that are not a power of two in [256, 2048] run the same schedule on cuFFT.)
 Spectral space is distributed over ky in +-ky symmetric sets, so the transposed operand
 u^(kz, +-ky, kx) the reference's `.T` projection needs (FlashUniform.py:281) is always rank-local.
 """
 
 from __future__ import annotations
-
-import os
 
 import numpy as np
 import torch
@@ -36,6 +35,7 @@ def ky_ownership(n: int, nranks: int) -> np.ndarray:
     return own
 
 
+PACK_SMS = 16  # SMs left to the exchange kernel (2 single-warp CTAs each) by the persistent transform kernels
 WS_SEND = 8  # FAVA_WS_USER0 + {0,1,2}: per-component slab buffers (weight -> in-place 2-D FFT)
 WS_RECV = 11  # + {0,1,2}: per-component ky-pencil receive buffers (peer-mapped on the other ranks)
 
@@ -47,19 +47,18 @@ class SlabPlan:
         if n % world or n % (2 * world):
             raise ValueError(f"grid size {n} must be divisible by 2 x {world} ranks")
         self.n, self.rank, self.world, self.dev = n, rank, world, dev
-        self.nxh = n // 2 + 1
+        self.pitch = device.spectral_pitch(n)  # complex elements per kx row
         self.nzl = n // world
         own = ky_ownership(n, world)
         self.nyl = own.shape[1]
         self.ky_of_dest = torch.from_numpy(own).to(dev)
-        self.ky_of_dest_host = np.ascontiguousarray(own, dtype=np.int32)
         mine = own[rank]
         inv = -np.ones(n, dtype=np.int32)
         inv[mine[mine >= 0]] = np.flatnonzero(mine >= 0).astype(np.int32)
         self.ky_of_local = torch.from_numpy(mine.copy()).to(dev)
         self.local_of_ky = torch.from_numpy(inv).to(dev)
-        send_bytes = 16 * self.nzl * n * self.nxh
-        recv_bytes = 16 * n * self.nyl * self.nxh
+        send_bytes = 16 * self.nzl * n * self.pitch
+        recv_bytes = 16 * n * self.nyl * self.pitch
         self.send = [device.workspace(WS_SEND + c, send_bytes, dev) for c in range(3)]
         self.recv = [device.workspace(WS_RECV + c, recv_bytes, dev) for c in range(3)]
         # peer mappings of every rank's receive buffers (CUDA IPC; NVLink P2P under NVSwitch)
@@ -67,7 +66,6 @@ class SlabPlan:
         gathered = [None] * world
         torch.distributed.all_gather_object(gathered, handles)
         self.peer_tables = []
-        self.peer_ptrs_host = []
         self._opened = []
         for c in range(3):
             ptrs = []
@@ -79,11 +77,14 @@ class SlabPlan:
                     self._opened.append(p)
                     ptrs.append(p)
             self.peer_tables.append(torch.tensor(ptrs, dtype=torch.int64, device=dev))
-            self.peer_ptrs_host.append(np.array(ptrs, dtype=np.uint64))
         self.sums = torch.zeros((3, n // 2 - 1), dtype=torch.float64, device=dev)
         self.tokens = [torch.zeros(1, dtype=torch.float32, device=dev) for _ in range(3)]
         self.comm_stream = torch.cuda.Stream(device=dev, priority=-1)  # NVLink exchange runs beside the HBM-bound kernels
+        self.token_stream = torch.cuda.Stream(device=dev, priority=-1)  # completion tokens: off the pack kernels' stream
+        # the exchange kernel needs a home while the persistent transform kernels own the SMs
+        device.reserve_sms(PACK_SMS, dev)
         self.ev_xy = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        self.ev_packed = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         self.ev_done = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         self.ev_mark = {k: torch.cuda.Event(enable_timing=True) for k in ("overlap", "fft_z", "bin")}
         dist.barrier()
@@ -116,42 +117,32 @@ def _plan(n: int, rank: int, world: int, dev) -> SlabPlan:
 
 
 def exchange(p: SlabPlan, c: int) -> None:
-    """Slab -> ky-pencil exchange of component c on the current stream.  FAVA_A2A_MODE selects the engine:
-    "tma" (default) = the fused pack kernel K5 on cp.async.bulk: 64 single-warp CTAs stream ky rows
-    global -> shared -> the owner's peer-mapped buffer and skip the columns outside the spectral disc
-    (measured at 8 GPUs, 1024^3: 1.37 ms per component, 685 GB/s of algorithmic bytes per GPU);
-    "ldst" = the same kernel with 16-byte loads/stores from registers (1.68 ms); "ce" = strided 2-D peer
-    copies on the copy engines (no SM use, no pruning, 1.59 ms)."""
-    mode = os.environ.get("FAVA_A2A_MODE", "tma")
-    if mode == "ce":
-        device.a2a_copy(p.send[c], p.peer_ptrs_host[c], p.ky_of_dest_host, p.rank, p.world, p.nzl, p.n, p.nyl, p.dev)
-    else:
-        device.a2a_pack(p.send[c], p.peer_tables[c], p.ky_of_dest, p.rank, p.world, p.nzl, p.n, p.nyl)
+    """Slab -> ky-pencil exchange of component c on the current stream: the fused pack kernel K5 streams ky rows
+    global -> shared -> the owner's peer-mapped buffer with TMA bulk copies and skips the columns outside the
+    spectral disc (measured at 8 GPUs, 1024^3: 1.37 ms per component; the register load/store form of the kernel
+    took 1.68 ms, strided copy-engine peer copies 1.59 ms - profiles/r01_a2a_engines_8gpu.txt)."""
+    device.a2a_pack(p.send[c], p.peer_tables[c], p.ky_of_dest, p.rank, p.world, p.nzl, p.n, p.nyl)
 
 
 def spectral_buffers(n: int, nz_local: int, dev) -> list[int]:
-    """Device addresses of the three per-component buffers the weighting + 2-D transform of a z-slab fill (real
-    [nz_local][n][2(n/2+1)] -> complex [nz_local][n][n/2+1] in place): the slab plan's send buffers on several
-    ranks, the workspaces of fava_ke_spectrum on one."""
+    """Device addresses of the three per-component buffers stages 1 + 2 of a z-slab fill (complex
+    [nz_local][n][pitch] afterwards): the slab plan's send buffers on several ranks, the workspaces of
+    fava_ke_spectrum on one."""
     world = dist.world_size()
     if world == 1:
-        return [device.workspace(4 + c, 16 * n * n * (n // 2 + 1), dev) for c in range(3)]  # WS_FFT1 + c
+        return [device.workspace(4 + c, device.spectral_bytes(n, n), dev) for c in range(3)]  # WS_FFT1 + c
     return _plan(n, dist.rank(), world, dev).send
 
 
-def spectrum_from_transformed_slabs(n: int, dev, epilogue=None, xy_done: bool = True) -> dict[str, np.ndarray]:
+def spectrum_from_transformed_slabs(n: int, dev, epilogue=None) -> dict[str, np.ndarray]:
     """Rest of the spectrum once `spectral_buffers` hold the 2-D transforms of this rank's planes (filled chunk
-    by chunk while the slab was still arriving from the host, stats.host_step): exchange, z transforms, binning.
-    `xy_done=False` (single rank): the buffers hold the weighted real fields only (written by the fused moment pass)
-    and the 2-D transforms run here first."""
+    by chunk while the slab was still arriving from the host, stats.host_step): exchange, z transforms, binning."""
     if dist.world_size() > 1:
         return slab_ke_spectrum(None, None, None, None, n, epilogue=epilogue, xy_done=True, dev=dev)
     w = spectral_buffers(n, n, dev)
     sums = torch.zeros((3, n // 2 - 1), dtype=torch.float64, device=dev)
     for c in range(3):
-        if not xy_done:
-            device.fft_xy(w[c], n, n, n, dev)
-        device.fft_z(w[c], n, n * (n // 2 + 1), dev)
+        device.ke_transform_z(w[c], n, n, None, dev)
     device.spectrum_bin(w[0], w[1], w[2], n, n, None, None, sums)
     if epilogue is not None:
         epilogue()
@@ -182,18 +173,22 @@ def slab_ke_spectrum(rho, ux, uy, uz, n: int, overlap=None, epilogue=None, xy_do
     p = _plan(n, rank, world, dev)
     cur = torch.cuda.current_stream(dev)
     if not xy_done:
-        device.ke_weight3(rho, ux, uy, uz, *p.send)
+        device.ke_transform_x(rho, ux, uy, uz, *p.send)
     for c in range(3):
         if not xy_done:  # else the send buffers already hold the 2-D transforms (spectrum_from_transformed_slabs)
-            device.fft_xy(p.send[c], p.nzl, n, n, dev)
+            device.ke_transform_y(p.send[c], p.nzl, n, dev)
         p.ev_xy[c].record(cur)
         with torch.cuda.stream(p.comm_stream):
             p.comm_stream.wait_event(p.ev_xy[c])
             exchange(p, c)
+            p.ev_packed[c].record(p.comm_stream)
+        with torch.cuda.stream(p.token_stream):
             # every rank's stores of component c into my receive buffer are complete once all ranks have
-            # passed this stream-ordered collective (each enqueues it after its own pack kernel)
+            # passed this stream-ordered collective (each enqueues it after its own pack kernel); it runs on its own
+            # stream so that the pack of component c+1 starts without waiting for it
+            p.token_stream.wait_event(p.ev_packed[c])
             dist.allreduce_sum_(p.tokens[c])
-            p.ev_done[c].record(p.comm_stream)
+            p.ev_done[c].record(p.token_stream)
     # `overlap` may be one callable or a list of them: the z-transform of component c is enqueued after the
     # c-th piece, so that it starts as soon as its exchange is done instead of queueing behind all the pieces
     pieces = list(overlap) if isinstance(overlap, (list, tuple)) else ([overlap] if overlap is not None else [])
@@ -205,7 +200,7 @@ def slab_ke_spectrum(rho, ux, uy, uz, n: int, overlap=None, epilogue=None, xy_do
                 extra()
             p.ev_mark["overlap"].record(cur)
         cur.wait_event(p.ev_done[c])
-        device.fft_z(p.recv[c], n, p.nyl * p.nxh, dev)
+        device.ke_transform_z(p.recv[c], n, p.nyl, p.ky_of_local, dev)
     p.ev_mark["fft_z"].record(cur)
     device.spectrum_bin(p.recv[0], p.recv[1], p.recv[2], n, p.nyl, p.ky_of_local, p.local_of_ky, p.sums)
     # shell sums and counts add across ranks; this collective also fences the receive buffers against

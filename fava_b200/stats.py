@@ -121,15 +121,7 @@ def slab_step(rho, ux, uy, uz, n: int, cell_volume: float, layer_volume: float, 
             mom, piv = pending[ax]
             out[ax] = slab_profiles_finish(mom, piv, ax, cell_volume, layer_volume, favre=favre, gather=False)
 
-    if spectrum and fuse_weighting(rho, axes, n):
-        # one rank, profiles + spectrum: the x/z moment pass also writes sqrt(rho) u_n for the transform, so the
-        # spectrum does not read rho,ux,uy,uz again (EXPERIMENTAL: opt-in with FAVA_FUSE_K4=1)
-        w = spec.spectral_buffers(n, n, rho.device)
-        pending[0], pending[2] = device.plane_moments_xz(rho, ux, uy, uz, weighted_out=w)
-        if 1 in axes:
-            pending[1] = slab_moments_local(rho, ux, uy, uz, 1)
-        out["spectrum"] = spec.spectrum_from_transformed_slabs(n, rho.device, epilogue=finish_profiles, xy_done=False)
-    elif spectrum:
+    if spectrum:
         out["spectrum"] = spec.slab_ke_spectrum(rho, ux, uy, uz, n, overlap=pieces, epilogue=finish_profiles)
     else:
         local_moments()
@@ -137,21 +129,12 @@ def slab_step(rho, ux, uy, uz, n: int, cell_volume: float, layer_volume: float, 
     return out
 
 
-def fuse_weighting(rho, axes, n: int) -> bool:
-    """Whether `slab_step` lets the x/z moment pass write the spectrum's weighted fields (one rank, cubic even grid,
-    x and z profiles requested, FAVA_FUSE_K4=1)."""
-    import os
-
-    return (os.environ.get("FAVA_FUSE_K4") == "1" and dist.world_size() == 1 and 0 in axes and 2 in axes
-            and tuple(rho.shape) == (n, n, n) and n % 2 == 0)
-
-
 def host_step(host, n: int, cell_volume: float, layer_volume: float, axes=(0, 1, 2), spectrum: bool = True,
               favre: bool = True, chunk_planes: int = 64, stage=None) -> dict:
     """`slab_step` for a snapshot that still lives in HOST memory (pinned tensors rho, ux, uy, uz of this rank's
     z-slab [nz_local][n][n]): the slab is copied to HBM in chunks of `chunk_planes` planes on a side stream and
     every chunk is consumed as soon as it has landed — plane moments accumulated about the pivots of the first
-    chunk, weighting + 2-D transforms written into the spectral buffers — so that all the HBM-bound work except
+    chunk, weighting + x and y transforms written into the spectral buffers — so that all the HBM-bound work except
     the z transforms and the binning hides behind the PCIe copy.  Same result dict as `slab_step`."""
     from fava_b200 import spectrum as spec
 
@@ -173,7 +156,7 @@ def host_step(host, n: int, cell_volume: float, layer_volume: float, axes=(0, 1,
             landed.append(ev)
 
     w = spec.spectral_buffers(n, nzl, dev) if spectrum else None
-    plane_bytes = 16 * n * (n // 2 + 1)  # one z-plane of a spectral buffer: complex [n][n/2+1]
+    plane_bytes = device.spectral_bytes(n, 1) if spectrum else 0  # one z-plane of a spectral buffer: complex [n][pitch]
     mom, piv = {}, {}
     for (a, b), ev in zip(chunks, landed):
         cur.wait_event(ev)
@@ -192,7 +175,7 @@ def host_step(host, n: int, cell_volume: float, layer_volume: float, axes=(0, 1,
                 mom[ax][:, a:b] = m
                 piv[ax][:, a:b] = pv
         if spectrum:
-            device.ke_weight_fft_xy(*part, *[p + a * plane_bytes for p in w])
+            device.ke_transform_xy(*part, *[p + a * plane_bytes for p in w])
     out = {}
 
     def finish_profiles():

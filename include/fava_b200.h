@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define FAVA_ABI_VERSION 1
+#define FAVA_ABI_VERSION 2
 
 /* status codes */
 #define FAVA_OK 0
@@ -94,15 +94,6 @@ int fava_plane_moments(fava_ctx* ctx, const void* d_rho, const void* d_ux, const
 int fava_plane_moments_xz(fava_ctx* ctx, const void* d_rho, const void* d_ux, const void* d_uy, const void* d_uz,
                           int dtype, int64_t nz, int64_t ny, int64_t nx, const double* d_piv_x,
                           const double* d_piv_z, double* d_mom_x, double* d_mom_z, void* stream);
-/* fava_plane_moments_xz that also writes K4's output (fava_ke_weight3: w_n = sqrt(rho) u_n, rows of `pitch` doubles,
- * FlashUniform.py:266-268) from the values it has in registers, so that a step computing profiles AND the spectrum
- * reads rho,ux,uy,uz once less.  Needs an even nx and 16-byte aligned fields / outputs.  EXPERIMENTAL in round 1:
- * compiled and parity-tested behind FAVA_FUSE_K4=1, not the default path yet. */
-int fava_plane_moments_xz_weight3(fava_ctx* ctx, const void* d_rho, const void* d_ux, const void* d_uy,
-                                  const void* d_uz, int dtype, int64_t nz, int64_t ny, int64_t nx,
-                                  const double* d_piv_x, const double* d_piv_z, double* d_mom_x, double* d_mom_z,
-                                  int64_t pitch, double* d_wx, double* d_wy, double* d_wz, void* stream);
-
 /* Block-list front end for FLASH block datasets [nblocks][nzb][nyb][nxb] (AMR or multi-block
  * uniform plt files).  For leaf l of the table: planes i=0..nrb-1 of block blk[l] normal to `axis`
  * contribute weight vf[l] to fine bins [ilo[l]+i*scale[l], ilo[l]+(i+1)*scale[l])
@@ -167,62 +158,74 @@ int fava_prolong(fava_ctx* ctx, const void* d_blocks, int dtype, int64_t nzb, in
 /* ---- kinetic-energy spectrum (reference: FlashUniform.kinetic_energy_spectra,
  *      fava/mesh/FLASH/FlashUniform.py:229-304) -------------------------------------------------- */
 
-/* Whole pipeline on one GPU for a cubic N^3 grid: w_n = sqrt(rho) u_n, 3-D FFT (cuFFT D2Z — the
- * one library call on this path), |u^|^2 / longitudinal projection / shell binning, shell means
- * x 4 pi k^2.  Outputs are HOST arrays of nbins = N/2 - 1 doubles (keys k,total,longitudinal,
- * transverse of the reference's dict). */
+/* Whole pipeline on one GPU for a cubic N^3 grid: w_n = sqrt(rho) u_n, 3-D FFT, |u^|^2 / longitudinal
+ * projection / shell binning, shell means x 4 pi k^2.  Power-of-two N in [256, 2048] take the hand-written
+ * transform (csrc/fft.cu); any other even N uses cuFFT D2Z/Z2Z - the one library call on this path.
+ * Outputs are HOST arrays of nbins = N/2 - 1 doubles (keys k,total,longitudinal,transverse of the
+ * reference's dict). */
 int fava_ke_spectrum(fava_ctx* ctx, const void* d_rho, const void* d_ux, const void* d_uy,
                      const void* d_uz, int dtype, int64_t n, double* h_k, double* h_total,
                      double* h_long, double* h_trans, void* stream);
 
-/* Building blocks of the same pipeline, exposed for the slab-decomposed (multi-GPU) driver. */
+/* Building blocks of the same pipeline, exposed for the slab-decomposed (multi-GPU) and the streamed
+ * (host-resident snapshot) drivers.  Spectral arrays are Hermitian halves, complex [..][..][pitch] with
+ * pitch = fava_spectral_pitch(n) complex numbers per kx row: n/2 on the hand-written path (the Nyquist column
+ * kx = n/2 lies beyond the last bin edge n/2 - 1.5, FlashUniform.py:273-276, and is not stored, which keeps
+ * every row a whole number of 128-byte lines), n/2 + 1 on the cuFFT path. */
+int64_t fava_spectral_pitch(int64_t n);
+int fava_fft_native_supported(int64_t n); /* 1: n is a power of two in [256, 2048] */
 
-/* w_n = sqrt(rho) * u_n for n = x,y,z in one pass (FlashUniform.py:266-268).  Inputs are `nrows` rows of
- * `nx` cells (a z-slab: nrows = nz_local*ny); outputs are real fp64 rows of `pitch` doubles
- * (pitch = 2*(nx/2+1): the padding an in-place real-to-complex transform needs). */
+/* Stage 1 of the transform of a z-slab [nz_local][n][n] of rho,ux,uy,uz (FlashUniform.py:266-268): on the
+ * hand-written path the weighting w_c = sqrt(rho) u_c FUSED with the x transform (the weighted real fields are
+ * never written), on the cuFFT path the weighting alone (real rows padded to 2 pitch doubles).  d_wx/wy/wz:
+ * one buffer of 16 nz_local n pitch bytes per component. */
+int fava_ke_transform_x(fava_ctx* ctx, const void* d_rho, const void* d_ux, const void* d_uy, const void* d_uz,
+                        int dtype, int64_t nz_local, int64_t n, double* d_wx, double* d_wy, double* d_wz,
+                        void* stream);
+/* Stage 2, per component, in place: completes the 2-D transform of the slab -> complex [nz_local][ky][kx]. */
+int fava_ke_transform_y(fava_ctx* ctx, double* d_w, int64_t nz_local, int64_t n, void* stream);
+/* Stage 3, per component, in place: transform along z of complex [n (z)][ny_local][pitch].  Row jl holds global
+ * ky index d_ky_of_local[jl] (NULL = this GPU holds every ky in order; -1 = padding row).  The hand-written pass
+ * skips columns outside the spectral disc and output rows outside the sphere: elements with
+ * kx^2 + ky^2 + kz^2 > (n/2 - 1.5)^2 are unspecified afterwards (no bin reads them). */
+int fava_ke_transform_z(fava_ctx* ctx, double* d_w, int64_t n, int64_t ny_local, const int32_t* d_ky_of_local,
+                        void* stream);
+
+/* The kernels behind the stages (also used directly by the tests). */
+
+/* K4: w_n = sqrt(rho) * u_n for n = x,y,z in one pass.  Inputs are `nrows` rows of `nx` cells; outputs are
+ * real fp64 rows of `pitch` doubles (pitch >= nx, even). */
 int fava_ke_weight3(fava_ctx* ctx, const void* d_rho, const void* d_ux, const void* d_uy, const void* d_uz,
                     int dtype, int64_t nrows, int64_t nx, int64_t pitch, double* d_wx, double* d_wy,
                     double* d_wz, void* stream);
-/* Hand-written line FFTs (csrc/fft.cu) for power-of-two N in [64, 4096]; 1 if this grid size takes them
- * (0 => the cuFFT entry points below are used; FAVA_FFT=cufft forces that). */
-int fava_fft_native_supported(int64_t n);
-/* x pass fused with the weighting: reads `nrows` rows of nx cells of rho,ux,uy,uz once and writes, per
- * component, the Hermitian half spectrum of sqrt(rho)*u along x: complex [nrows][nx/2+1] (FlashUniform.py:266-268). */
+/* x pass fused with the weighting (nx a power of two in [256, 2048], nrows a multiple of 8): reads `nrows`
+ * rows of nx cells of rho,ux,uy,uz once and writes, per component, kx = 0..nx/2-1 of the spectrum of
+ * sqrt(rho)*u along x into complex rows of `pitch` elements. */
 int fava_fft_x_weight3(fava_ctx* ctx, const void* d_rho, const void* d_ux, const void* d_uy, const void* d_uz,
-                       int dtype, int64_t nrows, int64_t nx, double* d_fx, double* d_fy, double* d_fz, void* stream);
-/* In-place complex FFT of length n along the middle axis of complex [nbatch][n][ncols] (y pass: ncols = nx/2+1,
- * nbatch = local z planes; z pass: ncols = ky rows x (nx/2+1), nbatch = 1).  prune_grid_n > 0 (z pass) skips
- * column tiles lying outside the spectral disc kx^2 + ky^2 <= (N/2-1.5)^2 of an N = prune_grid_n grid, the
- * columns being (ky row, kx) pairs with global ky index d_ky_of_local[row] (NULL = identity). */
-int fava_fft_cols(fava_ctx* ctx, double* d_data, int64_t n, int64_t ncols, int64_t nbatch, int64_t prune_grid_n,
-                  const int32_t* d_ky_of_local, void* stream);
-/* In-place batched 2-D FFT (cuFFT D2Z) of a slab: real [nz_local][ny][2*(nx/2+1)] (padded rows) ->
- * complex [nz_local][ny][nx/2+1] (interleaved re,im), transformed along x (halved) and y. */
-int fava_fft_xy(fava_ctx* ctx, double* d_data, int64_t nz_local, int64_t ny, int64_t nx, void* stream);
-/* K4 + the 2-D transform of a whole slab in one call (optionally in groups of FAVA_XY_GROUP z-planes; measured
- * slower on B200, see csrc/spectrum.cu).  Outputs as fava_fft_xy: complex [nz_local][n][n/2+1] per component. */
-int fava_ke_weight_fft_xy(fava_ctx* ctx, const void* d_rho, const void* d_ux, const void* d_uy, const void* d_uz,
-                          int dtype, int64_t nz_local, int64_t n, double* d_wx, double* d_wy, double* d_wz,
-                          void* stream);
-/* In-place c2c FFTs (cuFFT Z2Z) along the slowest axis of complex [nz][rows] (rows = ny_local*(nx/2+1)). */
-int fava_fft_z(fava_ctx* ctx, double* d_data, int64_t nz, int64_t rows, void* stream);
-/* Slab -> ky-pencil exchange, fused with the pack: rank `my_rank` holds complex [nz_local][n][nxh] after
- * fava_fft_xy; spectral space is distributed over ky in +-ky symmetric sets (so the transposed operand of
+                       int dtype, int64_t nrows, int64_t nx, int64_t pitch, double* d_fx, double* d_fy,
+                       double* d_fz, void* stream);
+/* In-place complex FFT of length n along dimension `line_dim` (1: d1, 2: d2) of complex [d2][d1][pitch], for
+ * the columns kx < ncols (a multiple of 8192/n).  prune_mode 0: every output; 1 (y pass): output rows with
+ * ky^2 + kx0^2 > (n/2-1.5)^2 are not written (kx0 = first column of the 8192/n-wide column tile); 2 (z pass,
+ * batch rows = ky rows with global index d_ky_of_batch[b], NULL = identity): tiles with ky^2 + kx0^2 beyond
+ * the disc are skipped and output rows beyond the sphere are not written. */
+int fava_fft_cols(fava_ctx* ctx, double* d_data, int64_t n, int64_t pitch, int64_t ncols, int64_t d1, int64_t d2,
+                  int line_dim, int prune_mode, const int32_t* d_ky_of_batch, void* stream);
+/* Persistent transform kernels leave `nsm` SMs free (default 0) so that a concurrent exchange kernel on
+ * another stream finds a home while they run. */
+int fava_reserve_sms(fava_ctx* ctx, int nsm);
+/* Slab -> ky-pencil exchange, fused with the pack: rank `my_rank` holds complex [nz_local][n][pitch] after
+ * stage 2; spectral space is distributed over ky in +-ky symmetric sets (so the transposed operand of
  * the longitudinal projection stays rank-local).  For every destination rank r the kernel gathers the ky
  * rows owned by r (d_ky_of_dest: [nranks][nyl] global ky indices, -1 = padding) and writes them straight
  * into r's receive buffer d_peer_recv[r] (peer-mapped device memory, or the local buffer when r ==
- * my_rank) at [my_rank*nz_local + z][row][kx] of a complex [n][nyl][nxh] array: no staging copy, the
- * NVLink stores overlap the gather. */
+ * my_rank) at [my_rank*nz_local + z][row][kx] of a complex [n][nyl][pitch] array: no staging copy, the
+ * NVLink stores overlap the gather (TMA bulk copies global -> shared -> peer global).  Columns outside the
+ * spectral disc are not sent. */
 int fava_a2a_pack(fava_ctx* ctx, const double* d_in, double* const* d_peer_recv, const int32_t* d_ky_of_dest,
                   int my_rank, int nranks, int64_t nz_local, int64_t n, int64_t nyl, void* stream);
-/* The same exchange on the copy engines: per destination the owned ky rows form (at most two) contiguous
- * runs, so the whole exchange is a handful of strided 2-D peer copies (one cudaMemcpy2DAsync per run) that
- * use no SM at all and overlap the HBM-bound kernels completely.  h_peer_recv / h_ky_of_dest are HOST arrays
- * (nranks device pointers; [nranks][nyl] ky indices). */
-int fava_a2a_copy(fava_ctx* ctx, const double* d_in, double* const* h_peer_recv, const int32_t* h_ky_of_dest,
-                  int my_rank, int nranks, int64_t nz_local, int64_t n, int64_t nyl, void* stream);
-/* Shell binning of one spectral sub-volume complex [n (kz)][ny_local][n/2+1] x 3 components of an n^3
- * transform scaled by `norm` (1/n^3, norm="forward").  Row jl holds global ky index d_ky_of_local[jl];
+/* Shell binning of one spectral sub-volume complex [n (kz)][ny_local][pitch] x 3 components of an n^3
+ * transform scaled by `norm` (1/n^3, norm="forward"), row pitch fava_spectral_pitch(n).  Row jl holds global ky index d_ky_of_local[jl];
  * d_local_of_ky[n] is the inverse (-1 = not held); both NULL = this GPU holds every ky in order.
  * d_sums: [3][n/2-1] = weighted sums of total, longitudinal, and the point counts (FlashUniform.py:273-293). */
 int fava_spectrum_bin(fava_ctx* ctx, const double* d_fx, const double* d_fy, const double* d_fz, int64_t n,

@@ -280,50 +280,72 @@ def test_data_returns_reference_layout(fava, tmp_path):
     assert m.data("no such field") is None
 
 
-@pytest.mark.parametrize("n,dtype", [(64, np.float32), (256, np.float64), (512, np.float32)])
-def test_native_fft_path_matches_cufft_path(cuda_device, monkeypatch, n, dtype):
-    """FAVA_FFT=native routes power-of-two grids through the hand-written line FFTs (x pass fused with the
-    weighting and fed by TMA bulk copies, strided y pass, disc-pruned z pass) instead of cuFFT.  Same spectra to 1e-13."""
-    import torch
-
-    from fava_b200 import _lib, device
-
-    monkeypatch.setenv("FAVA_FFT", "native")
-    assert _lib.load().fava_fft_native_supported(n) == 1 and _lib.load().fava_fft_native_supported(96) == 0
-    g = torch.Generator(device=cuda_device)
-    g.manual_seed(n)
-    tdt = torch.float64 if dtype == np.float64 else torch.float32
-    rho = (1.0 + 0.5 * torch.rand((n, n, n), generator=g, device=cuda_device, dtype=torch.float64)).to(tdt)
-    u = [(torch.randn((n, n, n), generator=g, device=cuda_device, dtype=torch.float64) + 0.3 * i).to(tdt) for i in range(3)]
-    native = device.ke_spectrum(rho, *u)
-    monkeypatch.setenv("FAVA_FFT_X", "plain")  # the two-CTA x kernel without the TMA prefetch
-    plain = device.ke_spectrum(rho, *u)
-    monkeypatch.delenv("FAVA_FFT_X")
-    monkeypatch.delenv("FAVA_FFT")
-    assert _lib.load().fava_fft_native_supported(n) == 0
-    library = device.ke_spectrum(rho, *u)
-    for k in ("k", "total", "longitudinal", "transverse"):
-        maxnorm_close(native[k], library[k], 1e-13, f"{k} n={n}")
-        assert np.array_equal(native[k], plain[k]), f"{k}: TMA-fed and plain x pass differ"
-
-
-def test_fft_x_pass_odd_row_count_and_small_grids(cuda_device):
-    """The persistent x pass on a row count that is odd and smaller than the grid of CTAs."""
+@pytest.mark.parametrize("n,dtype", [(256, np.float64), (256, np.float32), (512, np.float32)])
+def test_hand_written_transform_matches_torch_fft(cuda_device, n, dtype):
+    """Power-of-two grids take the hand-written passes (csrc/fft.cu): the fused weighting + x pass, the y pass and the
+    pruned z pass, each compared with torch.fft (cuFFT, test reference only) on the elements a bin can read."""
     import torch
 
     from fava_b200 import device
 
-    n = 128
-    for nrows in (1, 7, 300):
-        g = torch.Generator(device=cuda_device)
-        g.manual_seed(nrows)
-        f = [torch.rand((1, nrows, n), generator=g, device=cuda_device, dtype=torch.float64) + 0.5 for _ in range(4)]
-        out = [torch.zeros((nrows, n // 2 + 1), dtype=torch.complex128, device=cuda_device) for _ in range(3)]
-        device.fft_x_weight3(*f, *[o.data_ptr() for o in out])
-        for c in range(3):
-            ref = torch.fft.rfft(torch.sqrt(f[0][0]) * f[c + 1][0], dim=-1)
-            err = (out[c] - ref).abs().max().item() / ref.abs().max().item()
-            assert err <= 1e-13, (nrows, c, err)
+    assert device.fft_native_supported(n) and not device.fft_native_supported(96) and not device.fft_native_supported(128)
+    assert device.spectral_pitch(n) == n // 2 and device.spectral_pitch(96) == 49
+    nz = 8
+    g = torch.Generator(device=cuda_device)
+    g.manual_seed(n)
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    rho = (1.0 + 0.5 * torch.rand((nz, n, n), generator=g, device=cuda_device, dtype=torch.float64)).to(tdt)
+    u = [(torch.randn((nz, n, n), generator=g, device=cuda_device, dtype=torch.float64) + 0.3 * i).to(tdt) for i in range(3)]
+    pitch = n // 2
+    out = [torch.zeros((nz, n, pitch), dtype=torch.complex128, device=cuda_device) for _ in range(3)]
+    device.ke_transform_x(rho, *u, *[o.data_ptr() for o in out])
+    kmax2 = n * n // 4 - 3 * n // 2 + 2
+    k = torch.arange(n, device=cuda_device)
+    wn = torch.where(k < n // 2, k, k - n)
+    kx0 = (torch.arange(pitch, device=cuda_device) // (8192 // n)) * (8192 // n)  # first column of the column tile
+    for c in range(3):
+        w = torch.sqrt(rho.double()) * u[c].double()
+        ref = torch.fft.rfft(w, dim=-1)[..., :pitch]
+        maxnorm_close(torch.view_as_real(out[c]).cpu().numpy(), torch.view_as_real(ref).cpu().numpy(), 1e-13, f"x pass {c}")
+        device.ke_transform_y(out[c].data_ptr(), nz, n, cuda_device)
+        ref2 = torch.fft.fft(ref, dim=1)
+        keep = (wn[:, None] ** 2 + kx0[None, :] ** 2) <= kmax2  # rows the pruned y pass writes
+        got = torch.where(keep[None], out[c], torch.zeros_like(out[c]))
+        want = torch.where(keep[None], ref2, torch.zeros_like(ref2))
+        maxnorm_close(torch.view_as_real(got).cpu().numpy(), torch.view_as_real(want).cpu().numpy(), 1e-13, f"y pass {c}")
+    # z pass on a ky-pencil [n (z)][nyl][pitch] with a ky map: rows 3, n-3, 40 and a padding row
+    ky_rows = torch.tensor([3, n - 3, 40, -1], dtype=torch.int32, device=cuda_device)
+    z = (torch.randn((n, 4, pitch), generator=g, device=cuda_device, dtype=torch.float64)
+         + 1j * torch.randn((n, 4, pitch), generator=g, device=cuda_device, dtype=torch.float64))
+    ref3 = torch.fft.fft(z, dim=0)
+    device.ke_transform_z(z.data_ptr(), n, 4, ky_rows, cuda_device)
+    ky = torch.tensor([3, -3, 40, 10**6], device=cuda_device)
+    keep = (wn[:, None, None] ** 2 + ky[None, :, None] ** 2 + kx0[None, None, :] ** 2) <= kmax2
+    maxnorm_close(torch.view_as_real(torch.where(keep, z, torch.zeros_like(z))).cpu().numpy(),
+                  torch.view_as_real(torch.where(keep, ref3, torch.zeros_like(ref3))).cpu().numpy(), 1e-13, "z pass")
+
+
+@pytest.mark.parametrize("n", [256, 96])
+def test_spectrum_both_transform_paths_against_the_oracle(cuda_device, n):
+    """the oracle at 256^3 (hand-written transform path) and at 96^3 (cuFFT path, not a power of two)."""
+    import torch
+
+    from fava_b200 import device
+
+    full = synth.uniform_fields((n, n, n), names=FIELDS, seed=31 + n, u0=1.5)
+    want = orc.kinetic_energy_spectra({k: orc.load_like_reference(v) for k, v in full.items()}, (n, n, n))
+    t = [torch.from_numpy(full[k].copy()).to(cuda_device) for k in FIELDS]
+    got = device.ke_spectrum(*t)
+    for key in ("k", "total", "longitudinal", "transverse"):
+        maxnorm_close(got[key], want[key], RTOL, f"{key} n={n}")
+    again = device.ke_spectrum(*t)
+    assert all(np.array_equal(got[q], again[q]) for q in got)
+    t32 = [v.float() for v in t]  # plt files hold f32
+    full32 = {k: v.astype(np.float32) for k, v in full.items()}
+    want32 = orc.kinetic_energy_spectra({k: orc.load_like_reference(v) for k, v in full32.items()}, (n, n, n))
+    got32 = device.ke_spectrum(*t32)
+    for key in ("total", "longitudinal", "transverse"):
+        maxnorm_close(got32[key], want32[key], RTOL, f"{key} n={n} f32")
 
 
 def test_staging_file_and_host_paths_are_byte_exact(cuda_device, tmp_path):

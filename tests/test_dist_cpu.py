@@ -33,6 +33,12 @@ def _worker(rank: int, world: int, port: int, q):
         assert torch.equal(b, torch.full((3, 4), 1.0, dtype=torch.float64))
         cat = dist.all_gather_cat(t, dim=1)
         assert cat.shape == (3, 8) and torch.equal(cat[:, :4], torch.ones(3, 4, dtype=torch.float64))
+        # uneven z-slabs (7 planes over 2 ranks: 4 + 3): axis-z profiles [rows][local planes] concatenate ragged
+        a, b2 = dist.parallel_range(7)
+        prof = torch.arange(a, b2, dtype=torch.float64).repeat(2, 1)
+        whole = dist.all_gather_cat(prof, dim=1)
+        assert whole.shape == (2, 7) and torch.equal(whole[0], torch.arange(7, dtype=torch.float64))
+        assert torch.equal(dist.all_gather_cat(torch.arange(a, b2)), torch.arange(7))
         rows = dist.all_gather_rows(t)
         assert len(rows) == 2 and float(rows[1][0, 0]) == 2.0
         # ragged gather to the root (z-slabs / block ranges of different length)

@@ -137,3 +137,33 @@ def test_synthetic_flash_file_schema(tmp_path):
         d = f["dens"][()].astype(np.float64)
         child0 = d[gid[b, 7] - 1].reshape(2, 2, 2, 2, 2, 2).mean(axis=(1, 3, 5))
         assert np.allclose(d[b][:2, :2, :2], child0, rtol=1e-6)
+
+
+def test_append_survives_a_failed_flush_and_an_unreadable_file(tmp_path, monkeypatch):
+    """The result cache (Model.save_to_hdf5, mode "a") re-writes the file on close: a failure in the middle must leave
+    the previous contents intact (write-to-temp + rename), and a corrupt file must not block later runs."""
+    import os
+
+    path = tmp_path / "results.h5"
+    with h5lite.File(path, "w") as f:
+        f.create_dataset("a", data=np.arange(5.0))
+    real_replace = os.replace
+
+    def boom(src, dst):
+        raise OSError("disk full")
+
+    monkeypatch.setattr(os, "replace", boom)
+    try:
+        with h5lite.File(path, "a") as f:
+            f.create_dataset("b", data=np.arange(3.0))
+    except OSError:
+        pass
+    monkeypatch.setattr(os, "replace", real_replace)
+    assert [p.name for p in tmp_path.iterdir()] == ["results.h5"]  # no temp file left behind
+    with h5lite.File(path) as f:
+        assert np.array_equal(f["a"][()], np.arange(5.0)) and "b" not in f
+    path.write_bytes(b"\x89HDF\r\n\x1a\n" + b"\0" * 40)  # truncated
+    with h5lite.File(path, "a") as f:
+        f.create_dataset("c", data=np.arange(2.0))
+    with h5lite.File(path) as f:
+        assert np.array_equal(f["c"][()], np.arange(2.0))

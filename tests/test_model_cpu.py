@@ -78,21 +78,3 @@ def test_save_to_hdf5_roundtrip(tmp_path):
         assert np.array_equal(f["reynolds stresses"]["tensor"]["Rxx"][()], np.zeros(3))
         assert np.array_equal(f["reynolds stresses"]["radius"][()], np.arange(4.0))
         assert float(f["scalars"]["time"][()]) == 2.0
-
-
-def test_fused_weighting_is_opt_in_and_single_rank_only(monkeypatch):
-    """stats.fuse_weighting: the fused moment + weighting pass is used only on request (FAVA_FUSE_K4=1), on one rank,
-    for a cubic even grid and when both the x and z profiles are wanted (they come from that pass)."""
-    import torch
-
-    from fava_b200 import stats
-
-    rho = torch.empty((8, 8, 8))
-    monkeypatch.delenv("FAVA_FUSE_K4", raising=False)
-    assert not stats.fuse_weighting(rho, (0, 1, 2), 8)
-    monkeypatch.setenv("FAVA_FUSE_K4", "1")
-    assert stats.fuse_weighting(rho, (0, 1, 2), 8) and stats.fuse_weighting(rho, (2, 0), 8)
-    assert not stats.fuse_weighting(rho, (0, 1), 8)          # no z profile: the x-only pass is a different kernel
-    assert not stats.fuse_weighting(torch.empty((4, 8, 8)), (0, 1, 2), 8)  # a z-slab of a larger grid
-    monkeypatch.setenv("FAVA_FUSE_K4", "0")
-    assert not stats.fuse_weighting(rho, (0, 1, 2), 8)

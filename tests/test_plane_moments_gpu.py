@@ -4,7 +4,6 @@ Tolerance (BASELINE.json north_star): fp64 profiles within 1e-12 relative, max-n
 max|a-b| <= 1e-12 * max|b|.
 """
 
-import os
 
 import numpy as np
 import pytest
@@ -201,36 +200,3 @@ def test_fused_xz_pass_matches_single_axis_passes(cuda_device, dtype, shape):
     a, _ = device.plane_moments_xz(*t)
     b, _ = device.plane_moments_xz(*t)
     assert torch.equal(a[0], b[0])
-
-
-@pytest.mark.skipif(os.environ.get("FAVA_EXPERIMENTAL") != "1",
-                    reason="opt-in path (FAVA_FUSE_K4=1), not yet the default: run with FAVA_EXPERIMENTAL=1 (DESIGN.md section 7)")
-@pytest.mark.parametrize("n,dtype", [(64, torch.float64), (96, torch.float32)])
-def test_fused_weighting_pass_equals_separate_passes(cuda_device, monkeypatch, n, dtype):
-    """fava_plane_moments_xz_weight3: same moments as fava_plane_moments_xz, same weighted fields as fava_ke_weight3,
-    and the resident step with FAVA_FUSE_K4=1 returns bitwise what it returns without."""
-    from fava_b200 import device, stats
-
-    g = torch.Generator(device=cuda_device)
-    g.manual_seed(n)
-    f = [(torch.rand((n, n, n), generator=g, device=cuda_device, dtype=torch.float64) + 0.5).to(dtype) for _ in range(4)]
-    pitch = 2 * (n // 2 + 1)
-    wt = [torch.zeros((n * n, pitch), dtype=torch.float64, device=cuda_device) for _ in range(3)]
-    device.ke_weight3(*f, *[t.data_ptr() for t in wt])
-    ref = [t.clone() for t in wt]
-    for t in wt:
-        t.zero_()
-    (mx0, px0), (mz0, pz0) = device.plane_moments_xz(*f)
-    (mx1, px1), (mz1, pz1) = device.plane_moments_xz(*f, weighted_out=[t.data_ptr() for t in wt])
-    assert torch.equal(mx0, mx1) and torch.equal(mz0, mz1) and torch.equal(px0, px1) and torch.equal(pz0, pz1)
-    for a, b in zip(ref, wt):
-        assert torch.equal(a, b)
-    cv, lv = 1.0 / n**3, 1.0 / n
-    plain = stats.slab_step(*f, n, cv, lv)
-    monkeypatch.setenv("FAVA_FUSE_K4", "1")
-    fused = stats.slab_step(*f, n, cv, lv)
-    for k in plain["spectrum"]:
-        assert np.array_equal(plain["spectrum"][k], fused["spectrum"][k]), k
-    for ax in (0, 1, 2):
-        for k in plain[ax]:
-            assert torch.equal(plain[ax][k], fused[ax][k]), (ax, k)

@@ -1,4 +1,4 @@
-"""Micro-benchmark of the slab exchange engines (run under torchrun on N GPUs): GB/s per GPU per direction."""
+"""Micro-benchmark of the slab exchange kernel alone (run under torchrun on N GPUs): GB/s per GPU per direction."""
 import os
 import sys
 from pathlib import Path
@@ -16,30 +16,23 @@ def main():
     dev = torch.device("cuda", local)
     n = int(os.environ.get("FAVA_A2A_N", "1024"))
     p = spectrum._plan(n, rank, world, dev)
-    nominal = 16.0 * p.nzl * (n - 1) * p.nxh * (world - 1) / world  # bytes leaving this GPU, unpruned
-    configs = [("ldst", 64, 512), ("ldst", 148, 128), ("ldst", 296, 128), ("ldst", 296, 256), ("ldst", 592, 128),
-               ("ldst", 148, 512), ("tma", 64, 32), ("tma", 148, 32), ("ce", 0, 0)]
-    for mode, ctas, thr in configs:
-        os.environ["FAVA_A2A_MODE"] = mode
-        os.environ["FAVA_A2A_CTAS"] = str(ctas)
-        os.environ["FAVA_A2A_THREADS"] = str(thr)
-        for _ in range(2):
-            spectrum.exchange(p, 0)
-        dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(5):
-            spectrum.exchange(p, 0)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1) / 5], device=dev)
-        dist.allreduce_max_(ms)
-        if rank == 0:
-            real = nominal * (1.0 if mode == "ce" else 0.79)
-            print(f"A2A world={world} n={n} mode={mode} ctas={ctas} threads={thr}: {ms.item():.3f} ms  "
-                  f"nominal {nominal / ms.item() / 1e6:.0f} GB/s  on-wire ~{real / ms.item() / 1e6:.0f} GB/s", flush=True)
-        dist.barrier()
+    nominal = 16.0 * p.nzl * (n - 1) * p.pitch * (world - 1) / world  # bytes leaving this GPU, unpruned
+    for _ in range(2):
+        spectrum.exchange(p, 0)
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        spectrum.exchange(p, 0)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / 5], device=dev)
+    dist.allreduce_max_(ms)
+    if rank == 0:
+        print(f"A2A world={world} n={n}: {ms.item():.3f} ms  nominal {nominal / ms.item() / 1e6:.0f} GB/s  "
+              f"on-wire ~{0.79 * nominal / ms.item() / 1e6:.0f} GB/s", flush=True)
+    dist.barrier()
     torch.distributed.destroy_process_group()
 
 

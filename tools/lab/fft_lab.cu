@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(RegPlan<LOGN>::M1* C, (C >= 8 ? 1 : 2))
         for (int m = 0; m < 16; ++m) v[m] = __ldcs(base + (int64_t)O::in_index(u, m) * rstride);
         if (MODE == 0) {
             __syncthreads();  // previous tile's exchange reads are complete
-            fft_regs_full<LOGN, C>(v, u, c, xb, t1, t2);
+            fft_regs_full<LOGN>(v, u, ColAddr<C>{c}, xb, t1, t2);
         }
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
@@ -107,13 +107,13 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
 }
 
 // LINE_DIM = which tensor dimension the transform runs along (1: y pass, 2: z pass); C = 8, 16 doubles per row
-template <int LOGN, int MODE, int LINE_DIM>
-__global__ void __launch_bounds__(RegPlan<LOGN>::M1 * 8, 1)
+template <int LOGN, int C, int MODE, int LINE_DIM>
+__global__ void __launch_bounds__(RegPlan<LOGN>::M1 * C, 1)
     k_cols_tma(const __grid_constant__ CUtensorMap tmap, double2* __restrict__ data, int64_t rstride, int64_t bstride,
                int ntile_cols, int64_t ntiles, const double2* __restrict__ t1, const double2* __restrict__ t2, Prune pr) {
     using P = RegPlan<LOGN>;
     using O = Owner<LOGN>;
-    constexpr int C = 8, N = P::N;
+    constexpr int N = P::N;
     constexpr int BOX = 256;  // rows per TMA box
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     double2* land = reinterpret_cast<double2*>(smem_raw);                          // [N][8] complex, 128 B rows
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(RegPlan<LOGN>::M1 * 8, 1)
         __syncthreads();  // landing buffer consumed (and the previous tile's exchange reads are complete)
         const int64_t tn = next_tile(t + gridDim.x);
         if (threadIdx.x == 0 && tn < ntiles) issue(tn);
-        if (MODE == 0) fft_regs_half<LOGN, C>(v, u, c, xb, t1, t2);
+        if (MODE == 0) fft_regs_half<LOGN>(v, u, ColAddr<C>{c}, xb, t1, t2);
         double2* base = data + b * bstride + kx0 + c;
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
@@ -181,6 +181,113 @@ __global__ void __launch_bounds__(RegPlan<LOGN>::M1 * 8, 1)
         }
         t = tn;
     }
+}
+
+
+// ---- x pass fused with the weighting: z = w[row a] + i w[row b], w = sqrt(rho) u_c; two-for-one real transform ----
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <typename T, int LOGN, int PAIRS>
+struct XLayout {
+    static constexpr int N = 1 << LOGN, M1 = N / 16, LINES = 3 * PAIRS, THREADS = LINES * M1, ROWS = 2 * PAIRS;
+    static constexpr int LP = line_pitch(N);
+    static constexpr size_t land_bytes = sizeof(T) * 4 * ROWS * N;
+    static constexpr size_t srho_bytes = sizeof(double) * ROWS * N;
+    static constexpr size_t xb_bytes = sizeof(double) * LINES * LP;
+    static constexpr size_t total = land_bytes + srho_bytes + xb_bytes + 16;
+};
+
+template <typename T, int LOGN, int PAIRS, int CTAS, int MODE>
+__global__ void __launch_bounds__(XLayout<T, LOGN, PAIRS>::THREADS, CTAS)
+    k_xpass(const T* __restrict__ rho, const T* __restrict__ ux, const T* __restrict__ uy, const T* __restrict__ uz,
+            int64_t ntiles, const double2* __restrict__ t1, const double2* __restrict__ t2, double2* __restrict__ fx,
+            double2* __restrict__ fy, double2* __restrict__ fz, int64_t out_pitch) {
+    using L = XLayout<T, LOGN, PAIRS>;
+    using P = RegPlan<LOGN>;
+    constexpr int N = L::N, M1 = L::M1;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T* land = reinterpret_cast<T*>(smem_raw);                                        // [4][ROWS][N]
+    double* srho = reinterpret_cast<double*>(smem_raw + L::land_bytes);               // [ROWS][N]
+    double* xb = reinterpret_cast<double*>(smem_raw + L::land_bytes + L::srho_bytes);  // [LINES][LP]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L::land_bytes + L::srho_bytes + L::xb_bytes);
+    const int line = threadIdx.x / M1, u = threadIdx.x - line * M1;
+    const int pair = line / 3, comp = line - 3 * pair;
+    const T* src[4] = {rho, ux, uy, uz};
+    double2* out = comp == 0 ? fx : (comp == 1 ? fy : fz);
+    const LineAddr at{line * L::LP};
+
+    auto issue = [&](int64_t t) {  // one thread: the 2 PAIRS rows of a tile are contiguous in every field
+        constexpr unsigned bytes = (unsigned)(sizeof(T) * L::ROWS * N);
+        mbar_expect_tx(bar, 4 * bytes);
+#pragma unroll
+        for (int f = 0; f < 4; ++f) bulk_load_1d(land + f * L::ROWS * N, src[f] + t * L::ROWS * N, bytes, bar);
+    };
+    int64_t t = blockIdx.x;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async;\n" ::: "memory");
+        if (t < ntiles) issue(t);
+    }
+    __syncthreads();
+    unsigned parity = 0;
+    for (; t < ntiles; t += gridDim.x) {
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+        for (int i = threadIdx.x; i < L::ROWS * N; i += L::THREADS) srho[i] = sqrt((double)land[i]);
+        __syncthreads();
+        double2 v[16];
+        {
+            const double* sa = srho + (2 * pair) * N;
+            const T* ua = land + ((comp + 1) * L::ROWS + 2 * pair) * N;
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                const int n = u + M1 * m;
+                v[m] = make_double2(sa[n] * (double)ua[n], sa[N + n] * (double)ua[N + n]);
+            }
+        }
+        __syncthreads();  // landing rows and sqrt(rho) consumed
+        if (threadIdx.x == 0 && t + gridDim.x < ntiles) issue(t + gridDim.x);
+        double2 e[8], o[8];
+        if (MODE == 0) {
+            fft_regs_half<LOGN>(v, u, at, xb, t1, t2);
+            split_two_for_one<LOGN>(v, u, at, xb, e, o);
+        } else {
+#pragma unroll
+            for (int m = 0; m < 8; ++m) e[m] = v[m], o[m] = v[m + 8];
+        }
+        const int64_t row_a = (t * PAIRS + pair) * 2;
+        double2* oa = out + row_a * out_pitch;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const int k = u + M1 * m;
+            __stcs(oa + k, e[m]);
+            __stcs(oa + out_pitch + k, o[m]);
+        }
+    }
+}
+
+template <typename T>
+__global__ void k_fill_fields(T* rho, T* ux, T* uy, T* uz, int64_t n, uint64_t seed) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t z = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(i + 1);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        rho[i] = (T)(1.0 + 0.5 * (double)(z & 0xffff) / 65536.0);
+        ux[i] = (T)((double)((z >> 16) & 0xffff) / 65536.0 - 0.5);
+        uy[i] = (T)((double)((z >> 32) & 0xffff) / 65536.0 - 0.5);
+        uz[i] = (T)((double)((z >> 48) & 0xffff) / 65536.0 - 0.5);
+    }
+}
+template <typename T>
+__global__ void k_weight_ref(const T* rho, const T* u, double* w, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        w[i] = sqrt((double)rho[i]) * (double)u[i];
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -197,7 +304,7 @@ __global__ void k_fill(double2* d, int64_t n, uint64_t seed) {
 template <int LOGN>
 static void make_tables(double2** d_t1, double2** d_t2) {
     using P = RegPlan<LOGN>;
-    std::vector<double2> t1(P::T1_LEN), t2(P::T2_LEN);
+    std::vector<double2> t1(P::T1_LEN), t2(P::T2_LEN > 0 ? P::T2_LEN : 1);
     const long double two_pi = 6.283185307179586476925286766559005768L;
     for (int q = 0; q < 16; ++q)
         for (int j = 0; j < P::M1; ++j) {
@@ -230,13 +337,14 @@ static EncodeTiled get_encode() {
     return (EncodeTiled)fn;
 }
 
-// data: complex [d2][d1][pitch]; box = 8 complex x 256 along line_dim
-static CUtensorMap make_map(double2* data, int64_t pitch, int64_t d1, int64_t d2, int line_dim) {
+// data: complex [d2][d1][pitch]; box = C complex x min(256, n) along line_dim
+static CUtensorMap make_map(double2* data, int64_t pitch, int64_t d1, int64_t d2, int line_dim, int C, int n) {
     static EncodeTiled enc = get_encode();
     CUtensorMap m;
+    const cuuint32_t rows = (cuuint32_t)std::min(256, n);
     cuuint64_t dims[3] = {(cuuint64_t)(2 * pitch), (cuuint64_t)d1, (cuuint64_t)d2};
     cuuint64_t strides[2] = {(cuuint64_t)(pitch * 16), (cuuint64_t)(pitch * 16 * d1)};
-    cuuint32_t box[3] = {16, line_dim == 1 ? 256u : 1u, line_dim == 2 ? 256u : 1u};
+    cuuint32_t box[3] = {(cuuint32_t)(2 * C), line_dim == 1 ? rows : 1u, line_dim == 2 ? rows : 1u};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, data, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -256,12 +364,11 @@ struct Shape {
     int64_t elems() const { return pitch * d1 * d2; }
 };
 
-constexpr int LOGN = 10;
-constexpr int N = 1 << LOGN;
 static int g_sms = 148;
 
-template <int C, int MODE>
+template <int LOGN, int C, int MODE>
 static void run_direct(double2* d, const Shape& s, const double2* t1, const double2* t2, Prune pr, int ctas_per_sm) {
+    constexpr int N = 1 << LOGN;
     const int ntc = (N / 2) / C;
     const int64_t ntiles = s.nbatch() * ntc;
     const size_t smem = sizeof(double2) * N * C;
@@ -272,38 +379,38 @@ static void run_direct(double2* d, const Shape& s, const double2* t1, const doub
     CK(cudaGetLastError());
 }
 
-template <int MODE>
+template <int LOGN, int MODE>
 static void run_tma(double2* d, const Shape& s, const double2* t1, const double2* t2, Prune pr) {
-    constexpr int C = 8;
+    constexpr int N = 1 << LOGN;
+    constexpr int C = 8192 / N;  // 512 threads x 16 points
     const int ntc = (N / 2) / C;
     const int64_t ntiles = s.nbatch() * ntc;
     const size_t smem = sizeof(double2) * N * C + sizeof(double) * N * C + 64;
-    CUtensorMap map = make_map(d, s.pitch, s.d1, s.d2, s.line_dim);
+    CUtensorMap map = make_map(d, s.pitch, s.d1, s.d2, s.line_dim, C, N);
     const int grid = (int)std::min<int64_t>(ntiles, (int64_t)g_sms);
     if (s.line_dim == 1) {
-        auto kern = k_cols_tma<LOGN, MODE, 1>;
+        auto kern = k_cols_tma<LOGN, C, MODE, 1>;
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, RegPlan<LOGN>::M1 * C, smem>>>(map, d, s.rstride(), s.bstride(), ntc, ntiles, t1, t2, pr);
     } else {
-        auto kern = k_cols_tma<LOGN, MODE, 2>;
+        auto kern = k_cols_tma<LOGN, C, MODE, 2>;
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, RegPlan<LOGN>::M1 * C, smem>>>(map, d, s.rstride(), s.bstride(), ntc, ntiles, t1, t2, pr);
     }
     CK(cudaGetLastError());
 }
 
-static void cufft_ref(double2* d, const Shape& s) {  // in place, all columns
+static void cufft_ref(double2* d, const Shape& s, int N) {  // in place, all columns
     cufftHandle h;
     int n[1] = {N};
+    int embed[1] = {N};
     if (s.line_dim == 1) {
-        int embed[1] = {N};
         if (cufftPlanMany(&h, 1, n, embed, (int)s.pitch, 1, embed, (int)s.pitch, 1, CUFFT_Z2Z, (int)s.pitch) != CUFFT_SUCCESS) exit(3);
         for (int64_t z = 0; z < s.d2; ++z) {
             cufftDoubleComplex* p = (cufftDoubleComplex*)(d + z * s.pitch * s.d1);
             if (cufftExecZ2Z(h, p, p, CUFFT_FORWARD) != CUFFT_SUCCESS) exit(3);
         }
     } else {
-        int embed[1] = {N};
         const int cols = (int)(s.pitch * s.d1);
         if (cufftPlanMany(&h, 1, n, embed, cols, 1, embed, cols, 1, CUFFT_Z2Z, cols) != CUFFT_SUCCESS) exit(3);
         if (cufftExecZ2Z(h, (cufftDoubleComplex*)d, (cufftDoubleComplex*)d, CUFFT_FORWARD) != CUFFT_SUCCESS) exit(3);
@@ -313,7 +420,7 @@ static void cufft_ref(double2* d, const Shape& s) {  // in place, all columns
 }
 
 // max |a - b| over the elements a pruned transform must produce, relative to max |b|
-static double compare(const std::vector<double2>& a, const std::vector<double2>& b, const Shape& s, Prune pr, int C) {
+static double compare(const std::vector<double2>& a, const std::vector<double2>& b, const Shape& s, Prune pr, int C, int N) {
     double err = 0, ref = 0;
     const int kmax2 = pr.kmax2;
     for (int64_t i2 = 0; i2 < s.d2; ++i2)
@@ -357,63 +464,148 @@ static float time_ms(F&& f, int reps = 5) {
     return best;
 }
 
-int main(int argc, char** argv) {
-    const int64_t nfull = argc > 1 ? atoll(argv[1]) : 1024;
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, 0));
-    g_sms = prop.multiProcessorCount;
-    printf("device %s, %d SMs\n", prop.name, g_sms);
+template <int LOGN>
+static void check_cols() {
+    constexpr int N = 1 << LOGN;
+    constexpr int CT = 8192 / N;
     double2 *t1, *t2;
     make_tables<LOGN>(&t1, &t2);
     const int kmax2 = N * N / 4 - 3 * N / 2 + 2;
-
-    // ---------------- correctness on small shapes -----------------------------------------------------------
-    for (int pitch : {513, 512}) {
-        for (int line_dim : {1, 2}) {
-            Shape s{pitch, line_dim == 1 ? (int64_t)N : 6, line_dim == 1 ? 3 : (int64_t)N, line_dim};
-            const int64_t ne = s.elems();
-            double2 *d_in, *d_ref, *d_out;
-            CK(cudaMalloc(&d_in, sizeof(double2) * ne));
-            CK(cudaMalloc(&d_ref, sizeof(double2) * ne));
-            CK(cudaMalloc(&d_out, sizeof(double2) * ne));
-            k_fill<<<1024, 256>>>(d_in, ne, 42);
-            CK(cudaMemcpy(d_ref, d_in, sizeof(double2) * ne, cudaMemcpyDeviceToDevice));
-            cufft_ref(d_ref, s);
-            std::vector<double2> h_ref(ne), h_out(ne);
-            CK(cudaMemcpy(h_ref.data(), d_ref, sizeof(double2) * ne, cudaMemcpyDeviceToHost));
-            for (int prm : {0, line_dim}) {
-                Prune pr{prm, kmax2, N};
-                auto check = [&](const char* name, int C, auto&& launch) {
-                    CK(cudaMemcpy(d_out, d_in, sizeof(double2) * ne, cudaMemcpyDeviceToDevice));
-                    launch();
-                    cudaError_t e = cudaDeviceSynchronize();
-                    if (e != cudaSuccess) {
-                        printf("CHECK %-12s pitch %d dim %d prune %d: CUDA error %s\n", name, pitch, line_dim, prm, cudaGetErrorString(e));
-                        exit(4);
-                    }
-                    CK(cudaMemcpy(h_out.data(), d_out, sizeof(double2) * ne, cudaMemcpyDeviceToHost));
-                    const double err = compare(h_out, h_ref, s, pr, C);
-                    printf("CHECK %-12s pitch %d dim %d prune %d: rel err %.3e %s\n", name, pitch, line_dim, prm, err,
-                           err < 1e-13 ? "ok" : "FAIL");
-                };
-                check("direct C8", 8, [&] { run_direct<8, 0>(d_out, s, t1, t2, pr, 1); });
-                check("direct C4", 4, [&] { run_direct<4, 0>(d_out, s, t1, t2, pr, 2); });
-                check("tma C8", 8, [&] { run_tma<0>(d_out, s, t1, t2, pr); });
+    const int pitch = N / 2;
+    for (int line_dim : {1, 2}) {
+        Shape s{pitch, line_dim == 1 ? (int64_t)N : 6, line_dim == 1 ? 3 : (int64_t)N, line_dim};
+        const int64_t ne = s.elems();
+        double2 *d_in, *d_ref, *d_out;
+        CK(cudaMalloc(&d_in, sizeof(double2) * ne));
+        CK(cudaMalloc(&d_ref, sizeof(double2) * ne));
+        CK(cudaMalloc(&d_out, sizeof(double2) * ne));
+        k_fill<<<1024, 256>>>(d_in, ne, 42);
+        CK(cudaMemcpy(d_ref, d_in, sizeof(double2) * ne, cudaMemcpyDeviceToDevice));
+        cufft_ref(d_ref, s, N);
+        std::vector<double2> h_ref(ne), h_out(ne);
+        CK(cudaMemcpy(h_ref.data(), d_ref, sizeof(double2) * ne, cudaMemcpyDeviceToHost));
+        for (int prm : {0, line_dim}) {
+            Prune pr{prm, kmax2, N};
+            CK(cudaMemcpy(d_out, d_in, sizeof(double2) * ne, cudaMemcpyDeviceToDevice));
+            run_tma<LOGN, 0>(d_out, s, t1, t2, pr);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) {
+                printf("CHECK cols N %d dim %d prune %d: CUDA error %s\n", N, line_dim, prm, cudaGetErrorString(e));
+                exit(4);
             }
-            CK(cudaFree(d_in));
-            CK(cudaFree(d_ref));
-            CK(cudaFree(d_out));
+            CK(cudaMemcpy(h_out.data(), d_out, sizeof(double2) * ne, cudaMemcpyDeviceToHost));
+            const double err = compare(h_out, h_ref, s, pr, CT, N);
+            printf("CHECK cols tma N %d C %d dim %d prune %d: rel err %.3e %s\n", N, CT, line_dim, prm, err, err < 1e-13 ? "ok" : "FAIL");
         }
+        CK(cudaFree(d_in));
+        CK(cudaFree(d_ref));
+        CK(cudaFree(d_out));
     }
+    CK(cudaFree(t1));
+    CK(cudaFree(t2));
+}
 
-    // ---------------- timing at full size ---------------------------------------------------------------------
-    for (int pitch : {513, 512, 520}) {
+template <typename T, int LOGN, int PAIRS, int CTAS, int MODE>
+static void run_x(const T* rho, const T* ux, const T* uy, const T* uz, int64_t nrows, const double2* t1, const double2* t2,
+                  double2* fx, double2* fy, double2* fz, int64_t pitch) {
+    using L = XLayout<T, LOGN, PAIRS>;
+    auto kern = k_xpass<T, LOGN, PAIRS, CTAS, MODE>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
+    const int64_t ntiles = nrows / L::ROWS;
+    const int grid = (int)std::min<int64_t>(ntiles, (int64_t)g_sms * CTAS);
+    kern<<<grid, L::THREADS, L::total>>>(rho, ux, uy, uz, ntiles, t1, t2, fx, fy, fz, pitch);
+    CK(cudaGetLastError());
+}
+
+template <typename T, int LOGN, int PAIRS, int CTAS>
+static void check_x(int64_t nrows_full) {
+    constexpr int N = 1 << LOGN;
+    using L = XLayout<T, LOGN, PAIRS>;
+    double2 *t1, *t2;
+    make_tables<LOGN>(&t1, &t2);
+    const int64_t pitch = N / 2;
+    {
+        const int64_t nrows = 96;  // divisible by 2 PAIRS for PAIRS in {1,2,4}... and 8
+        const int64_t ne = nrows * N;
+        T *rho, *ux, *uy, *uz;
+        CK(cudaMalloc(&rho, sizeof(T) * ne));
+        CK(cudaMalloc(&ux, sizeof(T) * ne));
+        CK(cudaMalloc(&uy, sizeof(T) * ne));
+        CK(cudaMalloc(&uz, sizeof(T) * ne));
+        k_fill_fields<T><<<256, 256>>>(rho, ux, uy, uz, ne, 99);
+        double2* f[3];
+        for (auto& p : f) CK(cudaMalloc(&p, sizeof(double2) * nrows * pitch));
+        run_x<T, LOGN, PAIRS, CTAS, 0>(rho, ux, uy, uz, nrows, t1, t2, f[0], f[1], f[2], pitch);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) {
+            printf("CHECK x N %d: CUDA error %s\n", N, cudaGetErrorString(e));
+            exit(4);
+        }
+        double* w;
+        double2* ref;
+        CK(cudaMalloc(&w, sizeof(double) * ne));
+        CK(cudaMalloc(&ref, sizeof(double2) * nrows * (N / 2 + 1)));
+        cufftHandle h;
+        int n[1] = {N};
+        if (cufftPlanMany(&h, 1, n, nullptr, 1, N, nullptr, 1, N / 2 + 1, CUFFT_D2Z, (int)nrows) != CUFFT_SUCCESS) exit(3);
+        const T* u[3] = {ux, uy, uz};
+        std::vector<double2> h_ref(nrows * (N / 2 + 1)), h_out(nrows * pitch);
+        for (int c = 0; c < 3; ++c) {
+            k_weight_ref<T><<<256, 256>>>(rho, u[c], w, ne);
+            if (cufftExecD2Z(h, w, (cufftDoubleComplex*)ref) != CUFFT_SUCCESS) exit(3);
+            CK(cudaDeviceSynchronize());
+            CK(cudaMemcpy(h_ref.data(), ref, sizeof(double2) * h_ref.size(), cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(h_out.data(), f[c], sizeof(double2) * h_out.size(), cudaMemcpyDeviceToHost));
+            double err = 0, mx = 0;
+            for (int64_t r = 0; r < nrows; ++r)
+                for (int k = 0; k < N / 2; ++k) {
+                    const double2 a = h_out[r * pitch + k], b = h_ref[r * (N / 2 + 1) + k];
+                    err = std::max(err, std::max(fabs(a.x - b.x), fabs(a.y - b.y)));
+                    mx = std::max(mx, std::max(fabs(b.x), fabs(b.y)));
+                }
+            printf("CHECK x %s N %d pairs %d ctas %d smem %zu comp %d: rel err %.3e %s\n", sizeof(T) == 8 ? "f64" : "f32", N, PAIRS,
+                   CTAS, (size_t)L::total, c, err / mx, err / mx < 1e-13 ? "ok" : "FAIL");
+        }
+        cufftDestroy(h);
+        for (auto p : {(void*)rho, (void*)ux, (void*)uy, (void*)uz, (void*)w, (void*)ref, (void*)f[0], (void*)f[1], (void*)f[2]}) CK(cudaFree(p));
+    }
+    if (nrows_full > 0) {
+        const int64_t ne = nrows_full * N;
+        T *rho, *ux, *uy, *uz;
+        CK(cudaMalloc(&rho, sizeof(T) * ne));
+        CK(cudaMalloc(&ux, sizeof(T) * ne));
+        CK(cudaMalloc(&uy, sizeof(T) * ne));
+        CK(cudaMalloc(&uz, sizeof(T) * ne));
+        k_fill_fields<T><<<4096, 256>>>(rho, ux, uy, uz, ne, 5);
+        double2* f[3];
+        for (auto& p : f) CK(cudaMalloc(&p, sizeof(double2) * nrows_full * pitch));
+        CK(cudaDeviceSynchronize());
+        const double gb = (4.0 * sizeof(T) + 24.0) * (double)ne / 1e9;
+        float ms = time_ms([&] { run_x<T, LOGN, PAIRS, CTAS, 1>(rho, ux, uy, uz, nrows_full, t1, t2, f[0], f[1], f[2], pitch); });
+        printf("TIME x %s N %d pairs %d ctas %d copy-only %8.3f ms %7.1f GB/s\n", sizeof(T) == 8 ? "f64" : "f32", N, PAIRS, CTAS, ms,
+               gb / (ms * 1e-3));
+        ms = time_ms([&] { run_x<T, LOGN, PAIRS, CTAS, 0>(rho, ux, uy, uz, nrows_full, t1, t2, f[0], f[1], f[2], pitch); });
+        printf("TIME x %s N %d pairs %d ctas %d fft       %8.3f ms %7.1f GB/s (algorithmic %0.1f GB)\n", sizeof(T) == 8 ? "f64" : "f32", N,
+               PAIRS, CTAS, ms, gb / (ms * 1e-3), gb);
+        fflush(stdout);
+        for (auto p : {(void*)rho, (void*)ux, (void*)uy, (void*)uz, (void*)f[0], (void*)f[1], (void*)f[2]}) CK(cudaFree(p));
+    }
+    CK(cudaFree(t1));
+    CK(cudaFree(t2));
+}
+
+static void time_cols(int64_t nfull, bool all) {
+    constexpr int LOGN = 10, N = 1024;
+    double2 *t1, *t2;
+    make_tables<LOGN>(&t1, &t2);
+    const int kmax2 = N * N / 4 - 3 * N / 2 + 2;
+    for (int pitch : {512}) {
         double2* d;
         const int64_t ne = (int64_t)pitch * N * nfull;
         CK(cudaMalloc(&d, sizeof(double2) * ne));
         k_fill<<<4096, 256>>>(d, ne, 7);
         CK(cudaDeviceSynchronize());
-        const double gb_full = 2.0 * 16.0 * (double)(N / 2) * N * nfull / 1e9;  // read + write of the kx < N/2 columns
+        const double gb_full = 2.0 * 16.0 * (double)(N / 2) * N * nfull / 1e9;
         for (int line_dim : {1, 2}) {
             Shape s{pitch, line_dim == 1 ? (int64_t)N : nfull, line_dim == 1 ? nfull : (int64_t)N, line_dim};
             for (int prm : {0, line_dim}) {
@@ -423,48 +615,62 @@ int main(int argc, char** argv) {
                            prm, name, ms, gb_full / (ms * 1e-3), gb_full);
                     fflush(stdout);
                 };
-                report("direct C8 copy", time_ms([&] { run_direct<8, 1>(d, s, t1, t2, pr, 1); }));
-                report("direct C8 copyx2", time_ms([&] { run_direct<8, 1>(d, s, t1, t2, pr, 2); }));
-                report("direct C4 copy", time_ms([&] { run_direct<4, 1>(d, s, t1, t2, pr, 2); }));
-                report("direct C4 copyx4", time_ms([&] { run_direct<4, 1>(d, s, t1, t2, pr, 4); }));
-                report("tma C8 copy", time_ms([&] { run_tma<1>(d, s, t1, t2, pr); }));
-                report("direct C8 fft", time_ms([&] { run_direct<8, 0>(d, s, t1, t2, pr, 1); }));
-                report("direct C4 fft", time_ms([&] { run_direct<4, 0>(d, s, t1, t2, pr, 2); }));
-                report("tma C8 fft", time_ms([&] { run_tma<0>(d, s, t1, t2, pr); }));
-            }
-            if (pitch == 513 || pitch == 512) {  // cuFFT on the same layout (all `pitch` columns)
-                cufftHandle h;
-                int n[1] = {N}, embed[1] = {N};
-                size_t work = 0;
-                cufftCreate(&h);
-                cufftResult r;
-                if (line_dim == 1) {
-                    long long nn[1] = {N}, em[1] = {N};
-                    r = cufftMakePlanMany64(h, 1, nn, em, pitch, 1, em, pitch, 1, CUFFT_Z2Z, pitch, &work);
-                    (void)n, (void)embed;
-                    if (r == CUFFT_SUCCESS) {
-                        float ms = time_ms([&] {
-                            for (int64_t z = 0; z < nfull; ++z) {
-                                cufftDoubleComplex* p = (cufftDoubleComplex*)(d + z * s.pitch * s.d1);
-                                cufftExecZ2Z(h, p, p, CUFFT_FORWARD);
-                            }
-                        }, 2);
-                        printf("TIME pitch %d dim 1 cuFFT per-plane plans %8.3f ms\n", pitch, ms);
-                    }
-                } else {
-                    long long nn[1] = {N}, em[1] = {N};
-                    const long long cols = (long long)pitch * nfull;
-                    r = cufftMakePlanMany64(h, 1, nn, em, cols, 1, em, cols, 1, CUFFT_Z2Z, cols, &work);
-                    if (r == CUFFT_SUCCESS) {
-                        float ms = time_ms([&] { cufftExecZ2Z(h, (cufftDoubleComplex*)d, (cufftDoubleComplex*)d, CUFFT_FORWARD); }, 3);
-                        printf("TIME pitch %d dim 2 cuFFT strided plan   %8.3f ms  %7.1f GB/s\n", pitch, ms,
-                               2.0 * 16.0 * (double)pitch * N * nfull / 1e9 / (ms * 1e-3));
-                    }
+                if (all) {
+                    report("direct C8 copy", time_ms([&] { run_direct<LOGN, 8, 1>(d, s, t1, t2, pr, 1); }));
+                    report("direct C8 fft", time_ms([&] { run_direct<LOGN, 8, 0>(d, s, t1, t2, pr, 1); }));
+                    report("tma C8 copy", time_ms([&] { run_tma<LOGN, 1>(d, s, t1, t2, pr); }));
                 }
-                cufftDestroy(h);
+                report("tma C8 fft", time_ms([&] { run_tma<LOGN, 0>(d, s, t1, t2, pr); }));
             }
         }
         CK(cudaFree(d));
+    }
+}
+
+int main(int argc, char** argv) {
+    const std::string what = argc > 1 ? argv[1] : "all";
+    const int64_t nfull = argc > 2 ? atoll(argv[2]) : 1024;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, 0));
+    g_sms = prop.multiProcessorCount;
+    printf("device %s, %d SMs, mode %s\n", prop.name, g_sms, what.c_str());
+    if (what == "prof") {  // for ncu: exactly one pruned y pass, one pruned z pass and one fused x pass at full size
+        constexpr int N = 1024;
+        double2 *t1, *t2;
+        make_tables<10>(&t1, &t2);
+        const int kmax2 = N * N / 4 - 3 * N / 2 + 2;
+        const int64_t ne = (int64_t)512 * N * nfull;
+        double2* f[3];
+        for (auto& p : f) CK(cudaMalloc(&p, sizeof(double2) * ne));
+        double *rho, *ux, *uy, *uz;
+        for (auto pp : {&rho, &ux, &uy, &uz}) CK(cudaMalloc(pp, sizeof(double) * N * N * nfull));
+        k_fill_fields<double><<<4096, 256>>>(rho, ux, uy, uz, (int64_t)N * N * nfull, 5);
+        run_x<double, 10, 1, 2, 0>(rho, ux, uy, uz, N * nfull, t1, t2, f[0], f[1], f[2], 512);
+        Shape sy{512, N, nfull, 1}, sz{512, nfull, N, 2};
+        run_tma<10, 0>(f[0], sy, t1, t2, Prune{1, kmax2, N});
+        run_tma<10, 0>(f[0], sz, t1, t2, Prune{2, kmax2, N});
+        CK(cudaDeviceSynchronize());
+        printf("PROF DONE\n");
+        return 0;
+    }
+    if (what == "all" || what == "cols") {
+        check_cols<8>();
+        check_cols<9>();
+        check_cols<10>();
+        check_cols<11>();
+        time_cols(nfull, true);
+    }
+    if (what == "all" || what == "x") {
+        check_x<double, 8, 4, 2>(0);
+        check_x<float, 8, 4, 2>(0);
+        check_x<double, 9, 2, 2>(0);
+        check_x<float, 9, 2, 2>(0);
+        check_x<double, 11, 1, 1>(0);
+        check_x<float, 11, 1, 1>(0);
+        check_x<float, 10, 1, 2>(1024 * nfull);
+        check_x<double, 10, 1, 2>(1024 * nfull);
+        check_x<double, 10, 2, 1>(1024 * nfull);
+        check_x<double, 10, 1, 1>(1024 * nfull);
     }
     printf("LAB DONE\n");
     return 0;
