@@ -111,7 +111,10 @@ SIGNATURES: dict[str, tuple] = {
          c_void_p],
     ),
     "fava_fft_cols": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_void_p, c_void_p]),
-    "fava_reserve_sms": (c_int, [c_void_p, c_int]),
+    "fava_fft_y_scatter": (
+        c_int,
+        [c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_i64, c_i64, c_int, c_void_p],
+    ),
     "fava_a2a_pack": (
         c_int,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_i64, c_i64, c_i64, c_void_p],

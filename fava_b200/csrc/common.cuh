@@ -73,7 +73,8 @@ struct fava_ctx {
     std::map<int64_t, void*> twiddles;  // twiddle tables of the hand-written FFT, per N (fft.cu)
     // TMA descriptors of the column passes, keyed by (buffer, pitch, d1, d2, line dim / tile shape)
     std::map<std::tuple<uintptr_t, int64_t, int64_t, int64_t, int>, CUtensorMap> tensor_maps;
-    int reserved_sms = 0;  // SMs the persistent transform kernels leave free for a concurrent exchange kernel
+    void* tile_counters = nullptr;  // 64 tile counters of the persistent column kernels, used in turn (fft.cu)
+    unsigned tile_counter_next = 0;
     fava::Staging* staging = nullptr;
 };
 
@@ -84,9 +85,6 @@ int ctx_workspace(fava_ctx* ctx, int slot, size_t bytes, void** out);
 
 // hand-written FFT path for this grid size?  (power of two in [256, 2048]; other even N use cuFFT)
 bool fft_native_supported(int64_t n);
-
-// SMs a persistent kernel of the transform may occupy
-inline int ctx_sms(const fava_ctx* ctx) { return ctx->num_sms - ctx->reserved_sms > 0 ? ctx->num_sms - ctx->reserved_sms : 1; }
 
 struct DeviceGuard {
     int prev = -1;

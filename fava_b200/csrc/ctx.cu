@@ -89,6 +89,7 @@ int fava_shutdown(fava_ctx* ctx) {
     if (ctx->staging) staging_destroy(ctx->staging);
     for (auto& kv : ctx->plans) cufftDestroy(kv.second);
     for (auto& kv : ctx->twiddles) cudaFree(kv.second);
+    if (ctx->tile_counters) cudaFree(ctx->tile_counters);
     for (int i = 0; i < WS_COUNT; ++i)
         if (ctx->ws[i]) cudaFree(ctx->ws[i]);
     delete ctx;

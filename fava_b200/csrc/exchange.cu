@@ -131,12 +131,6 @@ int fava_a2a_pack(fava_ctx* ctx, const double* d_in, double* const* d_peer_recv,
     return FAVA_OK;
 }
 
-int fava_reserve_sms(fava_ctx* ctx, int nsm) {
-    FAVA_REQUIRE(ctx && nsm >= 0 && nsm < ctx->num_sms, "fava_reserve_sms: bad argument");
-    ctx->reserved_sms = nsm;
-    return FAVA_OK;
-}
-
 int fava_workspace(fava_ctx* ctx, int slot, int64_t bytes, void** d_ptr_out) {
     FAVA_REQUIRE(ctx && d_ptr_out && bytes >= 0, "fava_workspace: bad argument");
     DeviceGuard g(ctx->device);

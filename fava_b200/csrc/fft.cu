@@ -21,6 +21,8 @@
 //                    OUTPUT rows no bin can read (ky^2 + kx0^2 > kmax^2, resp. kz^2 + ky^2 + kx0^2 > kmax^2): 11 % /
 //                    35 % of the traffic of the y / z pass.  Unwritten elements keep stale values; the binning
 //                    kernel never uses an element outside the sphere (spectrum.cu: k2 <= kmax2).
+//                    On several GPUs the y pass IS the slab -> pencil exchange: its output rows go straight into the
+//                    owners' peer-mapped receive buffers over NVLink (ColScatter), no send buffer, no pack kernel.
 //
 // Measured on B200 at 1024^3 (tools/lab/fft_lab.cu, profiles/r02_fft_lab*.txt): y pass 3.40 ms, z pass 2.58 ms per
 // component against 5.39 ms for cuFFT's strided passes; the results agree with cuFFT to 6e-16 (max-norm).
@@ -176,12 +178,26 @@ struct ColPrune {
 
 __device__ __forceinline__ int wavenumber(int k, int n) { return k < n / 2 ? k : k - n; }
 
+// Slab -> ky-pencil exchange FUSED into the y pass (several GPUs): output row ky of local plane z is not written back
+// in place but straight into the receive buffer of the rank that owns ky - a peer-mapped pointer (CUDA IPC, NVLink 5 /
+// NVSwitch) or local memory - at [me nz_local + z][row of ky on its owner][kx] of that rank's complex
+// [n][nyl][pitch] array, i.e. already in the layout the z pass and the binning kernel consume.  128-byte chunks per
+// quarter-warp; the NVLink stores of one tile overlap the transform of the next.
+struct ColScatter {
+    double2* const* peer_recv;   // [nranks] receive buffers
+    const int32_t* owner_of_ky;  // [n] rank that owns global ky row k (-1: nobody, the Nyquist row)
+    const int32_t* row_of_ky;    // [n] row index of k inside its owner's ky set
+    int me, nz_local, nyl, z_offset;  // z_offset: first local plane of this call (chunked slabs)
+};
+
 // data: complex [d2][d1][pitch]; LINE_DIM = 1: lines run along d1, batches are d2 (y pass);
 //                                LINE_DIM = 2: lines run along d2, batches are d1 (z pass).
-template <int LOGN, int LINE_DIM>
+template <int LOGN, int LINE_DIM, bool SCATTER = false>
 __global__ void __launch_bounds__(512, 1)
     k_fft_cols(const __grid_constant__ CUtensorMap tmap, double2* __restrict__ data, int64_t rstride, int64_t bstride,
-               int ntile_cols, int64_t ntiles, const double2* __restrict__ t1, const double2* __restrict__ t2, ColPrune pr) {
+               int ntile_cols, int64_t ntiles, const double2* __restrict__ t1, const double2* __restrict__ t2, ColPrune pr,
+               ColScatter sc, unsigned long long* __restrict__ tile_counter) {
+    static_assert(!SCATTER || LINE_DIM == 1, "the exchange is fused into the y pass");
     using P = RegPlan<LOGN>;
     using O = Owner<LOGN>;
     constexpr int N = P::N, C = 8192 / N;
@@ -190,8 +206,17 @@ __global__ void __launch_bounds__(512, 1)
     double2* land = reinterpret_cast<double2*>(col_smem);                        // [N][C] complex, rows of 16 C bytes
     double* xb = reinterpret_cast<double*>(col_smem + sizeof(double2) * N * C);  // [N][C] exchange words (8 bytes)
     uint64_t* bar = reinterpret_cast<uint64_t*>(col_smem + sizeof(double2) * N * C + sizeof(double) * N * C);
+    int64_t* next_slot = reinterpret_cast<int64_t*>(bar + 2);  // [2]: the tile a CTA works on / the one being prefetched
+    double2** dst_row = reinterpret_cast<double2**>(col_smem + sizeof(double2) * N * C + sizeof(double) * N * C + 64);  // [N]
     const int c = threadIdx.x % C, u = threadIdx.x / C;
     const ColAddr<C> at{c};
+    if (SCATTER) {  // where output row ky of plane 0 goes (rstride = pitch in the y pass)
+        for (int k = threadIdx.x; k < N; k += blockDim.x) {
+            const int r = sc.owner_of_ky[k];
+            dst_row[k] = r < 0 ? nullptr
+                               : sc.peer_recv[r] + (((int64_t)sc.me * sc.nz_local + sc.z_offset) * sc.nyl + sc.row_of_ky[k]) * rstride;
+        }
+    }
 
     auto tile_k2 = [&](int64_t t, int64_t* b_out, int* kx0_out) {  // kx0^2 (+ ky^2 in the z pass); -1 = skip the tile
         const int64_t b = t / ntile_cols;
@@ -207,12 +232,16 @@ __global__ void __launch_bounds__(512, 1)
         }
         return k2;
     };
-    auto next_tile = [&](int64_t t) {  // first tile >= t (in this CTA's sequence) that is not skipped
+    // Tiles are handed out by a global counter (one atomic per tile, by the CTA's elected thread): a CTA that starts late
+    // because another kernel still holds its SM simply takes fewer tiles, and pruned tiles cost nobody a turn.
+    auto next_tile = [&]() {  // one thread: next tile that is not skipped, ntiles when the work is exhausted
         int64_t b;
         int kx0;
-        for (; t < ntiles; t += gridDim.x)
-            if (tile_k2(t, &b, &kx0) >= 0) break;
-        return t;
+        for (;;) {
+            const int64_t t = (int64_t)atomicAdd(tile_counter, 1ull);
+            if (t >= ntiles) return ntiles;
+            if (tile_k2(t, &b, &kx0) >= 0) return t;
+        }
     };
     auto issue = [&](int64_t t) {  // one thread
         const int64_t b = t / ntile_cols;
@@ -225,14 +254,17 @@ __global__ void __launch_bounds__(512, 1)
         }
     };
 
-    int64_t t = next_tile(blockIdx.x);
     if (threadIdx.x == 0) {
         mbar_setup(bar);
-        if (t < ntiles) issue(t);
+        const int64_t t0 = next_tile();
+        next_slot[0] = t0;
+        if (t0 < ntiles) issue(t0);
     }
     __syncthreads();
     unsigned parity = 0;
-    while (t < ntiles) {
+    for (int it = 0;; ++it) {
+        const int64_t t = next_slot[it & 1];
+        if (t >= ntiles) break;
         int64_t b;
         int kx0;
         const int base2 = tile_k2(t, &b, &kx0);
@@ -242,22 +274,36 @@ __global__ void __launch_bounds__(512, 1)
 #pragma unroll
         for (int m = 0; m < 16; ++m) v[m] = land[O::in_index(u, m) * C + c];
         __syncthreads();  // landing buffer consumed (and the previous tile's exchange reads are complete)
-        const int64_t tn = next_tile(t + gridDim.x);
-        if (threadIdx.x == 0 && tn < ntiles) issue(tn);
-        fft_regs_half<LOGN>(v, u, at, xb, t1, t2);
-        double2* base = data + b * bstride + kx0 + c;
-#pragma unroll
-        for (int r = 0; r < 16; ++r) {
-            const int k = O::out_freq(u, r);
-            bool keep = true;
-            if (pr.mode) {
-                const int w = wavenumber(k, pr.n);
-                keep = w * w + base2 <= pr.kmax2;
-            }
-            if (keep) __stcs(base + (int64_t)k * rstride, v[r]);
+        if (threadIdx.x == 0) {  // the other threads read the slot in the next iteration, several barriers from here
+            const int64_t tn = next_tile();
+            next_slot[(it + 1) & 1] = tn;
+            if (tn < ntiles) issue(tn);
         }
-        t = tn;
+        fft_regs_half<LOGN>(v, u, at, xb, t1, t2);
+        if (SCATTER) {
+            const int64_t zoff = b * (int64_t)sc.nyl * rstride + kx0 + c;  // plane b of the destination's [z][row][kx]
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const int k = O::out_freq(u, r);
+                const int w = wavenumber(k, pr.n);
+                double2* row = dst_row[k];
+                if (row != nullptr && w * w + base2 <= pr.kmax2) row[zoff] = v[r];
+            }
+        } else {
+            double2* base = data + b * bstride + kx0 + c;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const int k = O::out_freq(u, r);
+                bool keep = true;
+                if (pr.mode) {
+                    const int w = wavenumber(k, pr.n);
+                    keep = w * w + base2 <= pr.kmax2;
+                }
+                if (keep) __stcs(base + (int64_t)k * rstride, v[r]);
+            }
+        }
     }
+    if (SCATTER) __threadfence_system();  // peer stores ordered before the kernel's completion is observed
 }
 
 // ---- host side -------------------------------------------------------------------------------------------------
@@ -320,7 +366,7 @@ static int launch_x(fava_ctx* ctx, const T* rho, const T* ux, const T* uy, const
     auto kern = k_fft_x_weight<T, LOGN, PAIRS, CTAS>;
     FAVA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
     const int64_t ntiles = nrows / L::ROWS;
-    const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)ctx_sms(ctx) * CTAS);
+    const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)ctx->num_sms * CTAS);
     kern<<<grid, L::THREADS, L::total, st>>>(rho, ux, uy, uz, ntiles, t1, t2, fx, fy, fz, pitch);
     FAVA_LAUNCHED();
     return FAVA_OK;
@@ -340,26 +386,39 @@ static int dispatch_x(fava_ctx* ctx, int l, const T* rho, const T* ux, const T* 
 
 template <int LOGN>
 static int launch_cols(fava_ctx* ctx, double2* data, int64_t pitch, int64_t ncols, int64_t d1, int64_t d2, int line_dim,
-                       const double2* t1, const double2* t2, ColPrune pr, cudaStream_t st) {
+                       const double2* t1, const double2* t2, ColPrune pr, cudaStream_t st, const ColScatter* sc = nullptr,
+                       int max_ctas = 0) {
     constexpr int N = 1 << LOGN, C = 8192 / N, BOX = N < 256 ? N : 256;
     if (ncols % C) return set_error(FAVA_EINVAL, "fava_fft_cols: %lld columns are not a multiple of %d", (long long)ncols, C);
     const int ntc = (int)(ncols / C);
     const int64_t nbatch = line_dim == 1 ? d2 : d1;
     const int64_t ntiles = nbatch * ntc;
     const int64_t rstride = line_dim == 1 ? pitch : pitch * d1, bstride = line_dim == 1 ? pitch * d1 : pitch;
-    const size_t smem = sizeof(double2) * N * C + sizeof(double) * N * C + 64;
+    const size_t smem = sizeof(double2) * N * C + sizeof(double) * N * C + 64 + (sc ? sizeof(double2*) * N : 0);
+    if (smem > 227 * 1024) return set_error(FAVA_EINVAL, "fava_fft_cols: n = %d needs %zu bytes of shared memory", N, smem);
     CUtensorMap map;
     int rc = get_tensor_map(ctx, data, pitch, d1, d2, line_dim, C, BOX, &map);
     if (rc) return rc;
-    const unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)ctx_sms(ctx));
-    if (line_dim == 1) {
+    int64_t ctas = ctx->num_sms;
+    if (max_ctas > 0) ctas = std::min<int64_t>(ctas, max_ctas);
+    const unsigned grid = (unsigned)std::min<int64_t>(ntiles, ctas);
+    const ColScatter none = {};
+    // a zeroed tile counter per launch: 64 counters used in turn, so that launches in flight on several streams differ
+    if (!ctx->tile_counters) FAVA_CHECK_CUDA(cudaMalloc(&ctx->tile_counters, sizeof(unsigned long long) * 64));
+    unsigned long long* counter = (unsigned long long*)ctx->tile_counters + (ctx->tile_counter_next++ & 63);
+    FAVA_CHECK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
+    if (sc) {
+        auto kern = k_fft_cols<LOGN, 1, true>;
+        FAVA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, 512, smem, st>>>(map, data, rstride, bstride, ntc, ntiles, t1, t2, pr, *sc, counter);
+    } else if (line_dim == 1) {
         auto kern = k_fft_cols<LOGN, 1>;
         FAVA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, 512, smem, st>>>(map, data, rstride, bstride, ntc, ntiles, t1, t2, pr);
+        kern<<<grid, 512, smem, st>>>(map, data, rstride, bstride, ntc, ntiles, t1, t2, pr, none, counter);
     } else {
         auto kern = k_fft_cols<LOGN, 2>;
         FAVA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, 512, smem, st>>>(map, data, rstride, bstride, ntc, ntiles, t1, t2, pr);
+        kern<<<grid, 512, smem, st>>>(map, data, rstride, bstride, ntc, ntiles, t1, t2, pr, none, counter);
     }
     FAVA_LAUNCHED();
     return FAVA_OK;
@@ -415,6 +474,33 @@ int fava_fft_cols(fava_ctx* ctx, double* d_data, int64_t n, int64_t pitch, int64
         case 9: return launch_cols<9>(ctx, (double2*)d_data, pitch, ncols, d1, d2, line_dim, t1, t2, pr, st);
         case 10: return launch_cols<10>(ctx, (double2*)d_data, pitch, ncols, d1, d2, line_dim, t1, t2, pr, st);
         default: return launch_cols<11>(ctx, (double2*)d_data, pitch, ncols, d1, d2, line_dim, t1, t2, pr, st);
+    }
+}
+
+int fava_fft_y_scatter(fava_ctx* ctx, double* d_data, int64_t n, int64_t nz_chunk, double* const* d_peer_recv,
+                       const int32_t* d_owner_of_ky, const int32_t* d_row_of_ky, int my_rank, int64_t nz_local, int64_t nyl,
+                       int64_t z_offset, int max_ctas, void* stream) {
+    FAVA_REQUIRE(ctx && d_data && d_peer_recv && d_owner_of_ky && d_row_of_ky, "fava_fft_y_scatter: NULL argument");
+    FAVA_REQUIRE(fft_native_supported(n), "fava_fft_y_scatter: n = %lld is not a power of two in [256, 2048]", (long long)n);
+    FAVA_REQUIRE(nz_chunk > 0 && z_offset >= 0 && z_offset + nz_chunk <= nz_local && nyl > 0 && my_rank >= 0,
+                 "fava_fft_y_scatter: bad plane range");
+    const int l = ilog2_pow2(n);
+    DeviceGuard g(ctx->device);
+    const double2 *t1, *t2;
+    int rc = get_tables(ctx, l, &t1, &t2);
+    if (rc) return rc;
+    ColPrune pr;
+    pr.mode = 1, pr.n = (int)n, pr.kmax2 = (int)(n * n / 4 - 3 * n / 2 + 2), pr.ky_of_batch = nullptr;
+    ColScatter sc;
+    sc.peer_recv = (double2* const*)d_peer_recv, sc.owner_of_ky = d_owner_of_ky, sc.row_of_ky = d_row_of_ky;
+    sc.me = my_rank, sc.nz_local = (int)nz_local, sc.nyl = (int)nyl, sc.z_offset = (int)z_offset;
+    cudaStream_t st = (cudaStream_t)stream;
+    double2* data = (double2*)d_data;
+    switch (l) {
+        case 8: return launch_cols<8>(ctx, data, n / 2, n / 2, n, nz_chunk, 1, t1, t2, pr, st, &sc, max_ctas);
+        case 9: return launch_cols<9>(ctx, data, n / 2, n / 2, n, nz_chunk, 1, t1, t2, pr, st, &sc, max_ctas);
+        case 10: return launch_cols<10>(ctx, data, n / 2, n / 2, n, nz_chunk, 1, t1, t2, pr, st, &sc, max_ctas);
+        default: return launch_cols<11>(ctx, data, n / 2, n / 2, n, nz_chunk, 1, t1, t2, pr, st, &sc, max_ctas);
     }
 }
 

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256)
 constexpr int kTS = 32;        // tile edge in kx and kz
 constexpr int kBinT = 256;     // threads per CTA (8 warps, 4 kz rows each)
 constexpr int kBinWarps = kBinT / 32;
-constexpr int kSlots = 64;     // shell span of one tile (<= 31*sqrt(2) + 2)
+constexpr int kSlots = 48;     // shell span of one tile (<= 31*sqrt(2) + 2 = 45.8)
 
 struct BinParams {
     int n, pitch, ny_local, nbins, kmax2, npairs;  // pitch = complex elements per kx row (N/2 or N/2+1)
@@ -446,6 +446,8 @@ int fava_spectrum_bin(fava_ctx* ctx, const double* d_fx, const double* d_fy, con
     p.norm2 = norm * norm;
     const size_t nb_pad = (size_t)((3 * p.nbins + 1) & ~1);
     const size_t dyn = sizeof(double) * (nb_pad + 3 * kBinWarps * kSlots) + 3 * sizeof(double2) * kTS * (kTS + 1);
+    // two CTAs per SM; a third one (80 registers, 72 KB: it fits) measured 6 % slower at 1024^3 - more groups in flight
+    // evict each other's paired tiles from L2 before their second use
     const int ncta = (int)std::min<int64_t>(p.ngroups, (int64_t)ctx->num_sms * 2);
     void* ws;
     rc = ctx_workspace(ctx, WS_PARTIALS, sizeof(double) * 3 * (size_t)p.nbins * ncta, &ws);

@@ -474,10 +474,14 @@ def ke_transform_xy(rho, ux, uy, uz, wx: int, wy: int, wz: int) -> None:
         ke_transform_y(w, nz, n, rho.device)
 
 
-def reserve_sms(nsm: int, dev=None) -> None:
-    """Persistent transform kernels leave `nsm` SMs to a concurrent exchange kernel (fava_reserve_sms)."""
-    ctx = get_context(dev)
-    _lib.check(ctx.lib.fava_reserve_sms(ctx.handle, int(nsm)), "fava_reserve_sms")
+def fft_y_scatter(w: int, n: int, nz_chunk: int, peer_table: torch.Tensor, owner_of_ky: torch.Tensor,
+                  row_of_ky: torch.Tensor, rank: int, nz_local: int, nyl: int, z_offset: int = 0, max_ctas: int = 0) -> None:
+    """Stage 2 fused with the slab -> pencil exchange (fava_fft_y_scatter): y transform of nz_chunk planes whose output
+    rows go straight into the owners' peer-mapped receive buffers."""
+    ctx = get_context(peer_table.device)
+    _lib.check(ctx.lib.fava_fft_y_scatter(ctx.handle, C.c_void_p(w), int(n), int(nz_chunk), _ptr(peer_table), _ptr(owner_of_ky),
+                                          _ptr(row_of_ky), int(rank), int(nz_local), int(nyl), int(z_offset), int(max_ctas),
+                                          _stream(peer_table)), "fava_fft_y_scatter")
 
 
 def a2a_pack(src: int, peer_table: torch.Tensor, ky_of_dest: torch.Tensor, rank: int, world: int, nz_local: int, n: int,

@@ -35,7 +35,18 @@ def ky_ownership(n: int, nranks: int) -> np.ndarray:
     return own
 
 
-PACK_SMS = 16  # SMs left to the exchange kernel (2 single-warp CTAs each) by the persistent transform kernels
+def exchange_ctas(world: int, num_sms: int = 148) -> int:
+    """Persistent CTAs (one per SM) of the y pass fused with the exchange.  The kernel turns out ~14.5 GB/s of pruned
+    output per SM (measured: 1024^3 y pass in 3.08 ms on 148 SMs); (N-1)/N of it leaves the GPU and NVLink carries
+    ~770 GB/s per direction, so more than 770 / (14.5 (N-1)/N) SMs only queue stores behind the link.  The other SMs
+    run the plane-profile kernels, the completion tokens (NCCL needs an SM of its own) and the z passes of earlier
+    components at the same time; the column kernels take their tiles from a counter, so sharing the GPU costs them no
+    tail.  Measured at 2 GPUs with every SM given to the exchange: tokens and profile kernels queued behind it and the
+    step was serial (26.4 ms against 23.3 ms for half the single-GPU time)."""
+    want = int(np.ceil(1.05 * 770.0 / (14.5 * (world - 1) / world)))
+    return min(want, num_sms - 16)
+
+
 WS_SEND = 8  # FAVA_WS_USER0 + {0,1,2}: per-component slab buffers (weight -> in-place 2-D FFT)
 WS_RECV = 11  # + {0,1,2}: per-component ky-pencil receive buffers (peer-mapped on the other ranks)
 
@@ -57,6 +68,15 @@ class SlabPlan:
         inv[mine[mine >= 0]] = np.flatnonzero(mine >= 0).astype(np.int32)
         self.ky_of_local = torch.from_numpy(mine.copy()).to(dev)
         self.local_of_ky = torch.from_numpy(inv).to(dev)
+        owner = -np.ones(n, dtype=np.int32)  # rank that owns global ky row k, and k's row inside that rank's set
+        row = np.zeros(n, dtype=np.int32)
+        for r in range(world):
+            held = np.flatnonzero(own[r] >= 0)
+            owner[own[r][held]] = r
+            row[own[r][held]] = held
+        self.owner_of_ky = torch.from_numpy(owner).to(dev)
+        self.row_of_ky = torch.from_numpy(row).to(dev)
+        self.native = device.fft_native_supported(n)  # the y pass itself scatters its rows to their owners
         send_bytes = 16 * self.nzl * n * self.pitch
         recv_bytes = 16 * n * self.nyl * self.pitch
         self.send = [device.workspace(WS_SEND + c, send_bytes, dev) for c in range(3)]
@@ -81,8 +101,6 @@ class SlabPlan:
         self.tokens = [torch.zeros(1, dtype=torch.float32, device=dev) for _ in range(3)]
         self.comm_stream = torch.cuda.Stream(device=dev, priority=-1)  # NVLink exchange runs beside the HBM-bound kernels
         self.token_stream = torch.cuda.Stream(device=dev, priority=-1)  # completion tokens: off the pack kernels' stream
-        # the exchange kernel needs a home while the persistent transform kernels own the SMs
-        device.reserve_sms(PACK_SMS, dev)
         self.ev_xy = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         self.ev_packed = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         self.ev_done = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
@@ -116,12 +134,23 @@ def _plan(n: int, rank: int, world: int, dev) -> SlabPlan:
     return _plans[key]
 
 
-def exchange(p: SlabPlan, c: int) -> None:
-    """Slab -> ky-pencil exchange of component c on the current stream: the fused pack kernel K5 streams ky rows
-    global -> shared -> the owner's peer-mapped buffer with TMA bulk copies and skips the columns outside the
-    spectral disc (measured at 8 GPUs, 1024^3: 1.37 ms per component; the register load/store form of the kernel
-    took 1.68 ms, strided copy-engine peer copies 1.59 ms - profiles/r01_a2a_engines_8gpu.txt)."""
-    device.a2a_pack(p.send[c], p.peer_tables[c], p.ky_of_dest, p.rank, p.world, p.nzl, p.n, p.nyl)
+def exchange(p: SlabPlan, c: int, z_offset: int = 0, nz_chunk: int | None = None) -> None:
+    """Stage 2 + slab -> ky-pencil exchange of component c on the current stream.
+    Hand-written path: ONE kernel - the y pass of planes [z_offset, z_offset + nz_chunk) stores every output row straight
+    into its owner's peer-mapped receive buffer over NVLink (fava_fft_y_scatter), so the transfer overlaps the transform
+    tile by tile and neither a send-side copy of the y-transformed slab nor a pack pass exists.
+    cuFFT path (grid not a power of two): in-place 2-D transform, then the pack kernel K5 streams the ky rows global ->
+    shared -> the owner's buffer with TMA bulk copies (whole slab only)."""
+    nz_chunk = p.nzl if nz_chunk is None else nz_chunk
+    if p.native:
+        src = p.send[c] + z_offset * device.spectral_bytes(p.n, 1)
+        device.fft_y_scatter(src, p.n, nz_chunk, p.peer_tables[c], p.owner_of_ky, p.row_of_ky, p.rank, p.nzl, p.nyl,
+                             z_offset=z_offset, max_ctas=exchange_ctas(p.world))
+    else:
+        if z_offset or nz_chunk != p.nzl:
+            raise ValueError("the cuFFT path exchanges whole slabs")
+        device.ke_transform_y(p.send[c], p.nzl, p.n, p.dev)
+        device.a2a_pack(p.send[c], p.peer_tables[c], p.ky_of_dest, p.rank, p.world, p.nzl, p.n, p.nyl)
 
 
 def spectral_buffers(n: int, nz_local: int, dev) -> list[int]:
@@ -153,8 +182,8 @@ def slab_ke_spectrum(rho, ux, uy, uz, n: int, overlap=None, epilogue=None, xy_do
                      dev=None) -> dict[str, np.ndarray]:
     """Spectrum of the global N^3 grid formed by the ranks' z-slabs; every rank returns the full dict.
 
-    Schedule: the exchange of component c (K5, NVLink-bound, on a side stream) overlaps the 2-D transforms
-    of component c+1 and whatever `overlap()` enqueues on the calling stream (bench.py and
+    Schedule: the y pass + exchange of the three components (NVLink-bound, on a side stream with a share of the SMs)
+    overlaps whatever `overlap()` enqueues on the calling stream (bench.py and
     stats.slab_step put the HBM-bound plane-profile kernels there); the z-transform of component c
     starts as soon as ITS exchange has completed on every rank.  `epilogue()` is enqueued after the binning
     kernel and before the host synchronises on the shell sums."""
@@ -175,17 +204,16 @@ def slab_ke_spectrum(rho, ux, uy, uz, n: int, overlap=None, epilogue=None, xy_do
     if not xy_done:
         device.ke_transform_x(rho, ux, uy, uz, *p.send)
     for c in range(3):
-        if not xy_done:  # else the send buffers already hold the 2-D transforms (spectrum_from_transformed_slabs)
-            device.ke_transform_y(p.send[c], p.nzl, n, dev)
-        p.ev_xy[c].record(cur)
+        p.ev_xy[c].record(cur)  # (hand-written path: marks the end of the x pass; the y pass is part of the exchange)
         with torch.cuda.stream(p.comm_stream):
             p.comm_stream.wait_event(p.ev_xy[c])
-            exchange(p, c)
+            if not xy_done:  # else the rows were scattered chunk by chunk as the slab arrived (stats.host_step)
+                exchange(p, c)
             p.ev_packed[c].record(p.comm_stream)
         with torch.cuda.stream(p.token_stream):
             # every rank's stores of component c into my receive buffer are complete once all ranks have
-            # passed this stream-ordered collective (each enqueues it after its own pack kernel); it runs on its own
-            # stream so that the pack of component c+1 starts without waiting for it
+            # passed this stream-ordered collective (each enqueues it after its own exchange kernel); it runs on its own
+            # stream so that the exchange of component c+1 starts without waiting for it
             p.token_stream.wait_event(p.ev_packed[c])
             dist.allreduce_sum_(p.tokens[c])
             p.ev_done[c].record(p.token_stream)

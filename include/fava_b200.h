@@ -211,11 +211,19 @@ int fava_fft_x_weight3(fava_ctx* ctx, const void* d_rho, const void* d_ux, const
  * the disc are skipped and output rows beyond the sphere are not written. */
 int fava_fft_cols(fava_ctx* ctx, double* d_data, int64_t n, int64_t pitch, int64_t ncols, int64_t d1, int64_t d2,
                   int line_dim, int prune_mode, const int32_t* d_ky_of_batch, void* stream);
-/* Persistent transform kernels leave `nsm` SMs free (default 0) so that a concurrent exchange kernel on
- * another stream finds a home while they run. */
-int fava_reserve_sms(fava_ctx* ctx, int nsm);
-/* Slab -> ky-pencil exchange, fused with the pack: rank `my_rank` holds complex [nz_local][n][pitch] after
- * stage 2; spectral space is distributed over ky in +-ky symmetric sets (so the transposed operand of
+/* Stage 2 on several GPUs = y pass FUSED with the slab -> ky-pencil exchange (hand-written path only): the planes
+ * [z_offset, z_offset + nz_chunk) of this rank's slab, given at d_data as complex [nz_chunk][n][n/2] (x-transformed),
+ * are transformed along y and every output row ky is stored straight into the receive buffer of the rank that owns
+ * it, d_peer_recv[d_owner_of_ky[ky]] (peer-mapped device memory, or local when that is my_rank), at
+ * [my_rank*nz_local + z][d_row_of_ky[ky]][kx] of that rank's complex [n][nyl][n/2] array - the layout stage 3
+ * consumes.  Rows nobody owns (d_owner_of_ky = -1: the Nyquist row) and rows outside the spectral disc are not sent.
+ * max_ctas > 0 limits the persistent grid (NVLink needs fewer SMs than HBM; the rest run other kernels).  The stores are
+ * complete on every rank once all ranks have passed a stream-ordered collective issued after this call. */
+int fava_fft_y_scatter(fava_ctx* ctx, double* d_data, int64_t n, int64_t nz_chunk, double* const* d_peer_recv,
+                       const int32_t* d_owner_of_ky, const int32_t* d_row_of_ky, int my_rank, int64_t nz_local,
+                       int64_t nyl, int64_t z_offset, int max_ctas, void* stream);
+/* Slab -> ky-pencil exchange as a kernel of its own (cuFFT path; the hand-written path fuses it into stage 2,
+ * fava_fft_y_scatter): rank `my_rank` holds complex [nz_local][n][pitch] after stage 2; spectral space is distributed over ky in +-ky symmetric sets (so the transposed operand of
  * the longitudinal projection stays rank-local).  For every destination rank r the kernel gathers the ky
  * rows owned by r (d_ky_of_dest: [nranks][nyl] global ky indices, -1 = padding) and writes them straight
  * into r's receive buffer d_peer_recv[r] (peer-mapped device memory, or the local buffer when r ==
