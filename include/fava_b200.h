@@ -21,6 +21,9 @@
  *   - dtype: FAVA_F32 (plt files) or FAVA_F64 (chk files); f32 is widened to f64 in registers,
  *     bit-identical to `.astype(np.float64)` (_flash.py:333).  All arithmetic is fp64.
  *   - reductions are deterministic: fixed-order two-level accumulation, no floating-point atomics.
+ *   - a fava_ctx serves ONE compute stream at a time (its scratch buffers, cached tables and staging ring are not
+ *     fenced between streams); the one supported concurrent pair is fava_fft_y_scatter on a side stream beside the
+ *     plane-moment kernels / fava_ke_transform_z on another (they share no scratch).  Use one context per device.
  */
 #ifndef FAVA_B200_H
 #define FAVA_B200_H
