@@ -67,6 +67,12 @@ SIGNATURES: dict[str, tuple] = {
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_i64, c_i64, c_void_p, c_void_p, c_void_p,
          c_void_p, c_void_p],
     ),
+    "fava_plane_moments_xyz_supported": (c_int, [c_i64, c_i64, c_i64]),
+    "fava_plane_moments_xyz": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_i64, c_i64, c_void_p, c_void_p, c_void_p,
+         c_void_p, c_void_p, c_void_p, c_void_p],
+    ),
     "fava_plane_moments_blocks": (
         c_int,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_i64, c_i64, c_int,

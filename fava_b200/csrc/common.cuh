@@ -52,7 +52,7 @@ int set_error(int code, const char* fmt, ...);
 constexpr int kNumSMsB200 = 148;
 
 enum WorkspaceSlot { WS_PARTIALS = 0, WS_TABLE = 1, WS_AUX = 2, WS_FFT0 = 3, WS_FFT1 = 4, WS_FFT2 = 5,
-                     WS_FFTIN = 6, WS_BINMAP = 7, WS_USER0 = FAVA_WS_USER0, WS_ITEMS0 = 16 /* +axis: cached block-list tables */,
+                     WS_YPART = 6 /* row partials of the three-axis moment pass */, WS_BINMAP = 7, WS_USER0 = FAVA_WS_USER0, WS_ITEMS0 = 16 /* +axis: cached block-list tables */,
                      WS_COUNT = FAVA_WS_NSLOTS };
 
 struct Staging;  // pinned ring + reader threads (staging.cu)
@@ -71,8 +71,7 @@ struct fava_ctx {
     std::string item_cache_key[3];
     std::string prolong_cache_key;  // same for the lattice table of fava_prolong (WS_TABLE)
     std::map<int64_t, void*> twiddles;  // twiddle tables of the hand-written FFT, per N (fft.cu)
-    // TMA descriptors of the column passes, keyed by (buffer, pitch, d1, d2, line dim / tile shape)
-    std::map<std::tuple<uintptr_t, int64_t, int64_t, int64_t, int>, CUtensorMap> tensor_maps;
+    std::map<std::string, CUtensorMap> tensor_maps;  // TMA descriptors, keyed by (base, dtype, dims, strides, box)
     void* tile_counters = nullptr;  // 64 tile counters of the persistent column kernels, used in turn (fft.cu)
     unsigned tile_counter_next = 0;
     fava::Staging* staging = nullptr;
@@ -82,6 +81,11 @@ namespace fava {
 
 // Grow-only device workspace owned by the context.
 int ctx_workspace(fava_ctx* ctx, int slot, size_t bytes, void** out);
+
+// Cached tiled TMA descriptor (cuTensorMapEncodeTiled through the runtime's driver entry point; no swizzle, no
+// interleave, 128-byte L2 promotion).  dims / box in elements, strides in bytes (rank - 1 of them), innermost first.
+int ctx_tensor_map(fava_ctx* ctx, const void* base, CUtensorMapDataType dtype, int rank, const uint64_t* dims,
+                   const uint64_t* strides_bytes, const uint32_t* box, CUtensorMap* out);
 
 // hand-written FFT path for this grid size?  (power of two in [256, 2048]; other even N use cuFFT)
 bool fft_native_supported(int64_t n);

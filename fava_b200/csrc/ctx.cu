@@ -42,6 +42,47 @@ int ctx_workspace(fava_ctx* ctx, int slot, size_t bytes, void** out) {
     return FAVA_OK;
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int ctx_tensor_map(fava_ctx* ctx, const void* base, CUtensorMapDataType dtype, int rank, const uint64_t* dims,
+                   const uint64_t* strides_bytes, const uint32_t* box, CUtensorMap* out) {
+    std::string key((const char*)&base, sizeof(base));
+    key.append((const char*)&dtype, sizeof(dtype));
+    key.append((const char*)dims, sizeof(uint64_t) * rank);
+    key.append((const char*)strides_bytes, sizeof(uint64_t) * (rank - 1));
+    key.append((const char*)box, sizeof(uint32_t) * rank);
+    auto it = ctx->tensor_maps.find(key);
+    if (it != ctx->tensor_maps.end()) {
+        *out = it->second;
+        return FAVA_OK;
+    }
+    static EncodeTiledFn enc = nullptr;
+    if (!enc) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        FAVA_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (!fn || q != cudaDriverEntryPointSuccess)
+            return set_error(FAVA_ECUDA, "cuTensorMapEncodeTiled is not available in this driver");
+        enc = (EncodeTiledFn)fn;
+    }
+    cuuint64_t d[5], sb[4];
+    cuuint32_t b[5], es[5];
+    for (int i = 0; i < rank; ++i) d[i] = dims[i], b[i] = box[i], es[i] = 1;
+    for (int i = 0; i + 1 < rank; ++i) sb[i] = strides_bytes[i];
+    CUtensorMap m;
+    const CUresult r = enc(&m, dtype, (cuuint32_t)rank, const_cast<void*>(base), d, sb, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return set_error(FAVA_ECUDA, "cuTensorMapEncodeTiled(rank %d, inner %llu, box %u) failed: CUresult %d", rank,
+                         (unsigned long long)dims[0], box[0], (int)r);
+    if (ctx->tensor_maps.size() > 256) ctx->tensor_maps.clear();  // buffers are few and long-lived; bound the cache anyway
+    ctx->tensor_maps[key] = m;
+    *out = m;
+    return FAVA_OK;
+}
+
 void staging_destroy(Staging* s);  // staging.cu
 
 }  // namespace fava

@@ -319,42 +319,13 @@ bool fft_native_supported(int64_t n) {
     return l >= 8 && l <= 11;
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
 // tensor map of complex [d2][d1][pitch] seen as doubles [d2][d1][2 pitch]; box = C complex x `rows` along the line dim
 static int get_tensor_map(fava_ctx* ctx, double2* data, int64_t pitch, int64_t d1, int64_t d2, int line_dim, int C, int rows,
                           CUtensorMap* out) {
-    const auto key = std::make_tuple((uintptr_t)data, pitch, d1, d2, line_dim * 100000 + C * 1000 + rows);
-    auto it = ctx->tensor_maps.find(key);
-    if (it != ctx->tensor_maps.end()) {
-        *out = it->second;
-        return FAVA_OK;
-    }
-    static EncodeTiledFn enc = nullptr;
-    if (!enc) {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        FAVA_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
-        if (!fn || q != cudaDriverEntryPointSuccess)
-            return set_error(FAVA_ECUDA, "cuTensorMapEncodeTiled is not available in this driver");
-        enc = (EncodeTiledFn)fn;
-    }
-    CUtensorMap m;
-    cuuint64_t dims[3] = {(cuuint64_t)(2 * pitch), (cuuint64_t)d1, (cuuint64_t)d2};
-    cuuint64_t strides[2] = {(cuuint64_t)(pitch * 16), (cuuint64_t)(pitch * 16 * d1)};
-    cuuint32_t box[3] = {(cuuint32_t)(2 * C), line_dim == 1 ? (cuuint32_t)rows : 1u, line_dim == 2 ? (cuuint32_t)rows : 1u};
-    cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, data, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS)
-        return set_error(FAVA_ECUDA, "cuTensorMapEncodeTiled(pitch %lld, %lld x %lld, box %d x %d) failed: CUresult %d",
-                         (long long)pitch, (long long)d1, (long long)d2, 2 * C, rows, (int)r);
-    if (ctx->tensor_maps.size() > 64) ctx->tensor_maps.clear();  // buffers are few and long-lived; bound the cache anyway
-    ctx->tensor_maps[key] = m;
-    *out = m;
-    return FAVA_OK;
+    const uint64_t dims[3] = {(uint64_t)(2 * pitch), (uint64_t)d1, (uint64_t)d2};
+    const uint64_t strides[2] = {(uint64_t)(pitch * 16), (uint64_t)(pitch * 16 * d1)};
+    const uint32_t box[3] = {(uint32_t)(2 * C), line_dim == 1 ? (uint32_t)rows : 1u, line_dim == 2 ? (uint32_t)rows : 1u};
+    return ctx_tensor_map(ctx, data, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, dims, strides, box, out);
 }
 
 template <typename T, int LOGN, int PAIRS, int CTAS>

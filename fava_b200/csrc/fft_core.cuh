@@ -281,7 +281,8 @@ __device__ __forceinline__ void fft_regs_half(double2 (&v)[16], int u, const Add
 // e[m] = A^[k] = (Z[k] + conj Z[N-k]) / 2 and o[m] = B^[k] = (Z[k] - conj Z[N-k]) / (2i).  8-byte exchange words.
 template <int LOGN, class Addr, class Sync = CtaSync>
 __device__ __forceinline__ void split_two_for_one(double2 (&v)[16], int u, const Addr& at, double* __restrict__ xb,
-                                                  double2 (&e)[8], double2 (&o)[8], const Sync& sync = Sync()) {
+                                                  double2 (&e)[8], double2 (&o)[8], const Sync& sync = Sync(),
+                                                  double2* mid = nullptr) {
     using P = RegPlan<LOGN>;
     using O = Owner<LOGN>;
     sync();  // the last reads of the transform's exchange are complete
@@ -295,6 +296,7 @@ __device__ __forceinline__ void split_two_for_one(double2 (&v)[16], int u, const
         are[m] = xb[at(k)];
         bre[m] = xb[at((P::N - k) & (P::N - 1))];
     }
+    if (mid) mid->x = xb[at(P::N / 2)];  // Z[N/2], the one element the pairs (k, N - k), k < N/2, leave out
     sync();
 #pragma unroll
     for (int r = 0; r < 16; ++r) xb[at(O::out_freq(u, r))] = v[r].y;
@@ -306,6 +308,7 @@ __device__ __forceinline__ void split_two_for_one(double2 (&v)[16], int u, const
         e[m] = make_double2(0.5 * (are[m] + bre[m]), 0.5 * (aim - bim));
         o[m] = make_double2(0.5 * (aim + bim), 0.5 * (bre[m] - are[m]));
     }
+    if (mid) mid->y = xb[at(P::N / 2)];
 }
 
 }  // namespace fftc

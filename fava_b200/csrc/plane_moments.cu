@@ -348,6 +348,163 @@ __global__ void k_finalize(const double* __restrict__ mom, const double* __restr
         }
 }
 
+
+// ---- all three axes from ONE read ---------------------------------------------------------------------------
+// The x/z pass above and the y pass read the snapshot once each (64 B/cell for the three profile sets).  This
+// kernel reads it once (32 B/cell): a cell's 13 terms are accumulated twice out of shared memory - once by the
+// thread that owns its COLUMN (x bins; the z bins follow from the per-plane column partials exactly as in the x/z
+// pass) and once by the warp that owns its ROW (y bins).
+//   work item = (z plane, strip of 256 columns); a persistent 512-thread CTA walks the item in tiles of 8 rows x 256
+//   columns x 4 fields, which arrive through 2-D tensor maps (cp.async.bulk.tensor.2d, one box per field) into a
+//   3-stage ring while earlier tiles are consumed;
+//   group A (256 threads): thread = column; 13 accumulators about the column's x pivot, kept in registers over the 128
+//   tiles of the item, one store of [13][256] partials per item -> k_reduce_partials / k_partials_to_planes;
+//   group B (8 warps): warp = row; lane l takes columns l, l+32, ... about the row's y pivot, then the 13 sums of the warp
+//   are reduced by a halving exchange (16 shuffle pairs instead of 65 for 13 butterflies: at every step a lane keeps half
+//   of its values and sends the other half) and lanes 0,2,..,24 store one 128-byte record per (z, strip, row)
+//   -> k_reduce_rows.  Fixed orders throughout: bitwise reproducible.
+// fp64 pipe ~55 %, shared-memory reads 64 B/cell, shuffles 4/cell: under the HBM time of 32 B/cell.
+constexpr int kXyzCols = 256, kXyzRows = 8, kXyzStages = 3, kXyzThreads = 512;
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// 13 (padded to 16) per-lane values -> lane l ends with the warp total of value (l >> 1) & 15
+__device__ __forceinline__ double warp_halving_reduce16(double (&v)[16], int lane) {
+#pragma unroll
+    for (int half = 8, mask = 16; half >= 1; half >>= 1, mask >>= 1) {
+        const bool up = (lane & mask) != 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (i < half) {
+                const double send = up ? v[i] : v[i + half];
+                const double keep = up ? v[i + half] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+            }
+        }
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kXyzThreads, 1)
+    k_moments_xyz(const __grid_constant__ CUtensorMap tm_rho, const __grid_constant__ CUtensorMap tm_ux,
+                  const __grid_constant__ CUtensorMap tm_uy, const __grid_constant__ CUtensorMap tm_uz, int nz, int ny, int nx,
+                  const double* __restrict__ piv_x, const double* __restrict__ piv_y, double* __restrict__ xpartial,
+                  double* __restrict__ ypartial) {
+    constexpr int TILE = kXyzRows * kXyzCols;  // cells of one field in a tile
+    extern __shared__ __align__(1024) unsigned char xyz_smem[];
+    T* ring = reinterpret_cast<T*>(xyz_smem);  // [stages][4][8][256]
+    uint64_t* full = reinterpret_cast<uint64_t*>(xyz_smem + sizeof(T) * kXyzStages * 4 * TILE);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const bool colgroup = tid < kXyzCols;
+    const int row = (tid - kXyzCols) >> 5;  // group B: the warp's row inside a tile
+    const int nstrips = nx / kXyzCols, tpi = ny / kXyzRows;
+    const int64_t nitems = (int64_t)nz * nstrips;
+    const int64_t my_items = blockIdx.x < nitems ? (nitems - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t total = my_items * tpi;
+
+    auto issue = [&](int64_t g) {  // one thread
+        const int64_t item = blockIdx.x + (g / tpi) * gridDim.x;
+        const int z = (int)(item / nstrips), strip = (int)(item - (int64_t)z * nstrips);
+        const int y0 = (int)(g % tpi) * kXyzRows;
+        const int s = (int)(g % kXyzStages);
+        T* dst = ring + (size_t)s * 4 * TILE;
+        mbar_expect_tx(&full[s], (unsigned)(sizeof(T) * 4 * TILE));
+        tma_load_2d(dst, &tm_rho, strip * kXyzCols, z * ny + y0, &full[s]);
+        tma_load_2d(dst + TILE, &tm_ux, strip * kXyzCols, z * ny + y0, &full[s]);
+        tma_load_2d(dst + 2 * TILE, &tm_uy, strip * kXyzCols, z * ny + y0, &full[s]);
+        tma_load_2d(dst + 3 * TILE, &tm_uz, strip * kXyzCols, z * ny + y0, &full[s]);
+    };
+    if (tid == 0) {
+        for (int s = 0; s < kXyzStages; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async;\n" ::: "memory");
+        for (int64_t g = 0; g < kXyzStages && g < total; ++g) issue(g);
+    }
+    __syncthreads();
+
+    Acc<kNM> ax;
+    double cx0 = 0.0, cx1 = 0.0, cx2 = 0.0;
+    for (int64_t g = 0; g < total; ++g) {
+        const int64_t item = blockIdx.x + (g / tpi) * gridDim.x;
+        const int z = (int)(item / nstrips), strip = (int)(item - (int64_t)z * nstrips);
+        const int tile = (int)(g % tpi), y0 = tile * kXyzRows;
+        const int s = (int)(g % kXyzStages);
+        const T* st = ring + (size_t)s * 4 * TILE;
+        if (colgroup && tile == 0) {
+            ax.clear();
+            const int64_t x = (int64_t)strip * kXyzCols + tid;
+            cx0 = piv_x[x], cx1 = piv_x[nx + x], cx2 = piv_x[2 * (int64_t)nx + x];
+        }
+        double cy0 = 0.0, cy1 = 0.0, cy2 = 0.0;
+        if (!colgroup) cy0 = piv_y[y0 + row], cy1 = piv_y[ny + y0 + row], cy2 = piv_y[2 * ny + y0 + row];
+        mbar_wait(&full[s], (unsigned)((g / kXyzStages) & 1));
+        if (colgroup) {
+#pragma unroll
+            for (int r = 0; r < kXyzRows; ++r) {
+                const int o = r * kXyzCols + tid;
+                ax.add((double)st[o], (double)st[TILE + o], (double)st[2 * TILE + o], (double)st[3 * TILE + o], cx0, cx1, cx2);
+            }
+            if (tile == tpi - 1) {
+                double* out = xpartial + (int64_t)z * kNM * nx + (int64_t)strip * kXyzCols + tid;
+#pragma unroll
+                for (int m = 0; m < kNM; ++m) out[(int64_t)m * nx] = ax.m[m];
+            }
+        } else {
+            Acc<kNM> ay;
+            ay.clear();
+#pragma unroll
+            for (int j = 0; j < kXyzCols / 32; ++j) {
+                const int o = row * kXyzCols + lane + 32 * j;
+                ay.add((double)st[o], (double)st[TILE + o], (double)st[2 * TILE + o], (double)st[3 * TILE + o], cy0, cy1, cy2);
+            }
+            double v[16];
+#pragma unroll
+            for (int m = 0; m < 16; ++m) v[m] = m < kNM ? ay.m[m] : 0.0;
+            const double tot = warp_halving_reduce16(v, lane);
+            const int m = (lane >> 1) & 15;
+            if ((lane & 1) == 0 && m < kNM)
+                ypartial[((((int64_t)z * nstrips + strip) * ny) + y0 + row) * 16 + m] = tot;
+        }
+        __syncthreads();  // every thread is done with stage s
+        if (tid == 0 && g + kXyzStages < total) issue(g + kXyzStages);
+    }
+}
+
+// y bins = sum over (z, strip) of the 128-byte row records, in a fixed order; one CTA per y.
+__global__ void __launch_bounds__(128)
+    k_reduce_rows(const double* __restrict__ ypartial, int64_t nrec, int64_t ny, double cells_per_bin, double* __restrict__ mom) {
+    const int64_t y = blockIdx.x;
+    double acc[kNM];
+#pragma unroll
+    for (int m = 0; m < kNM; ++m) acc[m] = 0.0;
+    for (int64_t q = threadIdx.x; q < nrec; q += blockDim.x) {
+        const double2* rec = reinterpret_cast<const double2*>(ypartial + (q * ny + y) * 16);
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            const double2 p = rec[i];
+            if (2 * i < kNM) acc[2 * i] += p.x;
+            if (2 * i + 1 < kNM) acc[2 * i + 1] += p.y;
+        }
+    }
+    __shared__ double sm[kNM][128];
+#pragma unroll
+    for (int m = 0; m < kNM; ++m) sm[m][threadIdx.x] = acc[m];
+    __syncthreads();
+    if (threadIdx.x < kNM) {
+        double s = 0.0;
+        for (int t = 0; t < 128; ++t) s += sm[threadIdx.x][t];
+        mom[(int64_t)threadIdx.x * ny + y] = s;
+    }
+    if (threadIdx.x == kNM) mom[(int64_t)kNM * ny + y] = cells_per_bin;
+}
+
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 
@@ -462,6 +619,45 @@ static int dispatch_dense(fava_ctx* ctx, const void* rho, const void* ux, const 
                                  piv, mom, accumulate, st);
 }
 
+template <typename T>
+static int launch_xyz(fava_ctx* ctx, const T* rho, const T* ux, const T* uy, const T* uz, int64_t nz, int64_t ny, int64_t nx,
+                      const double* piv_x, const double* piv_y, const double* piv_z, double* mom_x, double* mom_y,
+                      double* mom_z, cudaStream_t st) {
+    const int64_t nstrips = nx / kXyzCols;
+    void *wx, *wy;
+    int rc = ctx_workspace(ctx, WS_PARTIALS, sizeof(double) * (size_t)nz * kNM * nx, &wx);
+    if (rc) return rc;
+    rc = ctx_workspace(ctx, WS_YPART, sizeof(double) * 16 * (size_t)(nz * nstrips * ny), &wy);
+    if (rc) return rc;
+    const CUtensorMapDataType dt = sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    const uint64_t dims[2] = {(uint64_t)nx, (uint64_t)(nz * ny)};
+    const uint64_t strides[1] = {(uint64_t)nx * sizeof(T)};
+    const uint32_t box[2] = {(uint32_t)kXyzCols, (uint32_t)kXyzRows};
+    CUtensorMap tm[4];
+    const T* src[4] = {rho, ux, uy, uz};
+    for (int f = 0; f < 4; ++f) {
+        rc = ctx_tensor_map(ctx, src[f], dt, 2, dims, strides, box, &tm[f]);
+        if (rc) return rc;
+    }
+    const size_t smem = sizeof(T) * kXyzStages * 4 * kXyzRows * kXyzCols + 64;
+    auto kern = k_moments_xyz<T>;
+    FAVA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)std::min<int64_t>(nz * nstrips, ctx->num_sms);
+    kern<<<grid, kXyzThreads, smem, st>>>(tm[0], tm[1], tm[2], tm[3], (int)nz, (int)ny, (int)nx, piv_x, piv_y, (double*)wx,
+                                         (double*)wy);
+    FAVA_LAUNCHED();
+    const int64_t n = (int64_t)FAVA_NMOM * nx;
+    k_reduce_partials<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>((const double*)wx, (int)nz, nx, kNM, FAVA_NMOM, mom_x, 0,
+                                                                 (double)(nz * ny));
+    FAVA_LAUNCHED();
+    k_partials_to_planes<<<(unsigned)nz, 256, 0, st>>>((const double*)wx, nx, nz, (double)ny, piv_x, piv_z, mom_z,
+                                                      (double)(nx * ny));
+    FAVA_LAUNCHED();
+    k_reduce_rows<<<(unsigned)ny, 128, 0, st>>>((const double*)wy, nz * nstrips, ny, (double)(nz * nx), mom_y);
+    FAVA_LAUNCHED();
+    return FAVA_OK;
+}
+
 }  // namespace fava
 
 using namespace fava;
@@ -521,6 +717,30 @@ int fava_plane_moments_xz(fava_ctx* ctx, const void* d_rho, const void* d_ux, co
     if (dtype == FAVA_F64)
         return dispatch_xz<double, 4>(ctx, d_rho, d_ux, d_uy, d_uz, nz, ny, nx, d_piv_x, d_piv_z, d_mom_x, d_mom_z, st);
     return dispatch_xz<float, 8>(ctx, d_rho, d_ux, d_uy, d_uz, nz, ny, nx, d_piv_x, d_piv_z, d_mom_x, d_mom_z, st);
+}
+
+int fava_plane_moments_xyz_supported(int64_t nz, int64_t ny, int64_t nx) {
+    return (nz > 0 && nz * ny < (int64_t(1) << 31) && nx % kXyzCols == 0 && ny % kXyzRows == 0) ? 1 : 0;
+}
+
+int fava_plane_moments_xyz(fava_ctx* ctx, const void* d_rho, const void* d_ux, const void* d_uy, const void* d_uz, int dtype,
+                           int64_t nz, int64_t ny, int64_t nx, const double* d_piv_x, const double* d_piv_y,
+                           const double* d_piv_z, double* d_mom_x, double* d_mom_y, double* d_mom_z, void* stream) {
+    FAVA_REQUIRE(ctx && d_rho && d_ux && d_uy && d_uz && d_piv_x && d_piv_y && d_piv_z && d_mom_x && d_mom_y && d_mom_z,
+                 "fava_plane_moments_xyz: NULL argument");
+    FAVA_REQUIRE(dtype == FAVA_F32 || dtype == FAVA_F64, "fava_plane_moments_xyz: bad dtype %d", dtype);
+    FAVA_REQUIRE(fava_plane_moments_xyz_supported(nz, ny, nx),
+                 "fava_plane_moments_xyz: needs nx %% %d == 0 and ny %% %d == 0 (got %lldx%lldx%lld); use the per-axis passes",
+                 kXyzCols, kXyzRows, (long long)nz, (long long)ny, (long long)nx);
+    FAVA_REQUIRE(aligned_to(d_rho, 16) && aligned_to(d_ux, 16) && aligned_to(d_uy, 16) && aligned_to(d_uz, 16),
+                 "fava_plane_moments_xyz: fields must be 16-byte aligned");
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == FAVA_F64)
+        return launch_xyz<double>(ctx, (const double*)d_rho, (const double*)d_ux, (const double*)d_uy, (const double*)d_uz, nz,
+                                  ny, nx, d_piv_x, d_piv_y, d_piv_z, d_mom_x, d_mom_y, d_mom_z, st);
+    return launch_xyz<float>(ctx, (const float*)d_rho, (const float*)d_ux, (const float*)d_uy, (const float*)d_uz, nz, ny, nx,
+                             d_piv_x, d_piv_y, d_piv_z, d_mom_x, d_mom_y, d_mom_z, st);
 }
 
 int fava_plane_sum(fava_ctx* ctx, const void* d_field, int dtype, int64_t nz, int64_t ny, int64_t nx, int axis,

@@ -146,6 +146,27 @@ def plane_moments_xz(rho, ux, uy, uz):
     return (mom_x, piv_x), (mom_z, piv_z)
 
 
+def plane_moments_xyz_supported(shape) -> bool:
+    nz, ny, nx = (int(v) for v in shape)
+    return bool(_lib.load().fava_plane_moments_xyz_supported(nz, ny, nx))
+
+
+def plane_moments_xyz(rho, ux, uy, uz):
+    """Moments for all three axes from ONE pass over the fields (fava_plane_moments_xyz)
+    -> [(mom_x, piv_x), (mom_y, piv_y), (mom_z, piv_z)]."""
+    nz, ny, nx = _check_fields(rho, ux, uy, uz)
+    ctx = get_context(rho.device)
+    piv = [plane_pivots(ux, uy, uz, ax) for ax in (0, 1, 2)]
+    mom = [torch.empty((FAVA_NMOM, n), dtype=torch.float64, device=rho.device) for n in (nx, ny, nz)]
+    _lib.check(
+        ctx.lib.fava_plane_moments_xyz(ctx.handle, _ptr(rho), _ptr(ux), _ptr(uy), _ptr(uz), _dtype_code(rho), nz, ny, nx,
+                                       _ptr(piv[0]), _ptr(piv[1]), _ptr(piv[2]), _ptr(mom[0]), _ptr(mom[1]), _ptr(mom[2]),
+                                       _stream(rho)),
+        "fava_plane_moments_xyz",
+    )
+    return list(zip(mom, piv))
+
+
 def moments_repivot(moments: torch.Tensor, piv_old: torch.Tensor, piv_new: torch.Tensor) -> None:
     ctx = get_context(moments.device)
     nbins = int(moments.shape[1])

@@ -105,9 +105,15 @@ def slab_step(rho, ux, uy, uz, n: int, cell_volume: float, layer_volume: float, 
 
         return run
 
+    def moments_xyz():  # x, y and z bins from ONE pass over the slab
+        (pending[0], pending[1], pending[2]) = device.plane_moments_xyz(rho, ux, uy, uz)
+
     pieces = []
     todo = list(axes)
-    if 0 in todo and 2 in todo:
+    if set(todo) >= {0, 1, 2} and device.plane_moments_xyz_supported(rho.shape):
+        pieces.append(moments_xyz)
+        todo = []
+    elif 0 in todo and 2 in todo:
         pieces.append(moments_xz)
         todo = [ax for ax in todo if ax == 1]
     pieces += [moments_of(ax) for ax in todo]

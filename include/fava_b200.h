@@ -97,6 +97,14 @@ int fava_plane_moments(fava_ctx* ctx, const void* d_rho, const void* d_ux, const
 int fava_plane_moments_xz(fava_ctx* ctx, const void* d_rho, const void* d_ux, const void* d_uy, const void* d_uz,
                           int dtype, int64_t nz, int64_t ny, int64_t nx, const double* d_piv_x,
                           const double* d_piv_z, double* d_mom_x, double* d_mom_z, void* stream);
+/* All three profile sets from ONE pass over the fields (32 B/cell fp64 instead of 64): moments for axis x, y and z
+ * with the pivots of fava_plane_pivots (axis 0 / 1 / 2).  Needs nx % 256 == 0 and ny % 8 == 0
+ * (fava_plane_moments_xyz_supported); other shapes use fava_plane_moments_xz + fava_plane_moments. */
+int fava_plane_moments_xyz_supported(int64_t nz, int64_t ny, int64_t nx);
+int fava_plane_moments_xyz(fava_ctx* ctx, const void* d_rho, const void* d_ux, const void* d_uy, const void* d_uz,
+                           int dtype, int64_t nz, int64_t ny, int64_t nx, const double* d_piv_x, const double* d_piv_y,
+                           const double* d_piv_z, double* d_mom_x, double* d_mom_y, double* d_mom_z, void* stream);
+
 /* Block-list front end for FLASH block datasets [nblocks][nzb][nyb][nxb] (AMR or multi-block
  * uniform plt files).  For leaf l of the table: planes i=0..nrb-1 of block blk[l] normal to `axis`
  * contribute weight vf[l] to fine bins [ilo[l]+i*scale[l], ilo[l]+(i+1)*scale[l])

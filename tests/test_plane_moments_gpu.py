@@ -200,3 +200,28 @@ def test_fused_xz_pass_matches_single_axis_passes(cuda_device, dtype, shape):
     a, _ = device.plane_moments_xz(*t)
     b, _ = device.plane_moments_xz(*t)
     assert torch.equal(a[0], b[0])
+
+
+@pytest.mark.parametrize("shape,dtype", [((16, 64, 256), torch.float64), ((5, 8, 512), torch.float32), ((40, 136, 768), torch.float64)])
+def test_three_axis_pass_equals_per_axis_passes(cuda_device, shape, dtype):
+    """fava_plane_moments_xyz (one read of the fields) gives the profiles of the three per-axis calls, for shapes that
+    split unevenly over the persistent CTAs, f32 and f64, with a large mean (the pivots matter), bitwise repeatable."""
+    from fava_b200 import device
+
+    nz, ny, nx = shape
+    g = torch.Generator(device=cuda_device)
+    g.manual_seed(nz * 131 + nx)
+    f = [(torch.rand(shape, generator=g, device=cuda_device, dtype=torch.float64) + (0.5 if i == 0 else 25.0 * i)).to(dtype)
+         for i in range(4)]
+    assert device.plane_moments_xyz_supported(shape) and not device.plane_moments_xyz_supported((4, 12, 256))
+    assert not device.plane_moments_xyz_supported((4, 8, 384))
+    res = device.plane_moments_xyz(*f)
+    cv = 1.0 / (nz * ny * nx)
+    for axis, (mom, piv) in enumerate(res):
+        lv = 1.0 / shape[2 - axis]
+        got = device.moments_finalize(mom, piv, cv, lv)
+        want = device.plane_profiles(*f, axis, cv, lv)
+        for k in want:
+            maxnorm_close(got[k].cpu().numpy(), want[k].cpu().numpy(), rtol=1e-13, what=f"xyz {k} axis {axis} {shape}")
+    again = device.plane_moments_xyz(*f)
+    assert all(torch.equal(a[0], b[0]) for a, b in zip(res, again))

@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "fft_core.cuh"
@@ -267,6 +268,95 @@ __global__ void __launch_bounds__(XLayout<T, LOGN, PAIRS>::THREADS, CTAS)
             const int k = u + M1 * m;
             __stcs(oa + k, e[m]);
             __stcs(oa + out_pitch + k, o[m]);
+        }
+    }
+}
+
+
+// ---- x pass, one ROW per warp-line: real row of N points = complex transform of N/2 points of the even/odd packing ----
+template <typename T, int LOGN>
+struct XRowLayout {
+    static constexpr int N = 1 << LOGN, H = N / 2, LOGH = LOGN - 1, M1 = H / 16, THREADS = 3 * M1;
+    static constexpr int LP = line_pitch(H);
+    static constexpr size_t land_bytes = sizeof(T) * 4 * N;
+    static constexpr size_t srho_bytes = sizeof(double) * N;
+    static constexpr size_t xb_bytes = sizeof(double) * 3 * LP;
+    static constexpr size_t total = land_bytes + srho_bytes + xb_bytes + 16;
+};
+template <typename T> struct Vec2;
+template <> struct Vec2<double> { typedef double2 type; };
+template <> struct Vec2<float> { typedef float2 type; };
+
+template <typename T, int LOGN, int CTAS, int MODE>
+__global__ void __launch_bounds__(XRowLayout<T, LOGN>::THREADS, CTAS)
+    k_xrow(const T* __restrict__ rho, const T* __restrict__ ux, const T* __restrict__ uy, const T* __restrict__ uz, int64_t nrows,
+           const double2* __restrict__ t1, const double2* __restrict__ t2, const double2* __restrict__ tw,
+           double2* __restrict__ fx, double2* __restrict__ fy, double2* __restrict__ fz, int64_t out_pitch) {
+    using L = XRowLayout<T, LOGN>;
+    constexpr int N = L::N, H = L::H, M1 = L::M1, LOGH = L::LOGH;
+    typedef typename Vec2<T>::type T2;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T* land = reinterpret_cast<T*>(smem_raw);                                        // [4][N]
+    double* srho = reinterpret_cast<double*>(smem_raw + L::land_bytes);               // [N]
+    double* xb = reinterpret_cast<double*>(smem_raw + L::land_bytes + L::srho_bytes);  // [3][LP]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L::land_bytes + L::srho_bytes + L::xb_bytes);
+    const int comp = threadIdx.x / M1, u = threadIdx.x - comp * M1;
+    const T* src[4] = {rho, ux, uy, uz};
+    double2* out = comp == 0 ? fx : (comp == 1 ? fy : fz);
+    const LineAddr at{comp * L::LP};
+    const LineSync<M1> line_sync{comp};
+
+    auto issue = [&](int64_t r) {
+        constexpr unsigned bytes = (unsigned)(sizeof(T) * N);
+        mbar_expect_tx(bar, 4 * bytes);
+#pragma unroll
+        for (int f = 0; f < 4; ++f) bulk_load_1d(land + f * N, src[f] + r * N, bytes, bar);
+    };
+    int64_t row = blockIdx.x;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async;\n" ::: "memory");
+        if (row < nrows) issue(row);
+    }
+    __syncthreads();
+    unsigned parity = 0;
+    for (; row < nrows; row += gridDim.x) {
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+        for (int i = threadIdx.x; i < N; i += L::THREADS) srho[i] = sqrt((double)land[i]);
+        __syncthreads();
+        double2 v[16];
+        {
+            const double2* s2 = reinterpret_cast<const double2*>(srho);
+            const T2* u2 = reinterpret_cast<const T2*>(land + (comp + 1) * N);
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                const int idx = u + M1 * m;  // complex point idx = real samples 2 idx, 2 idx + 1
+                const double2 s = s2[idx];
+                const T2 a = u2[idx];
+                v[m] = make_double2(s.x * (double)a.x, s.y * (double)a.y);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && row + gridDim.x < nrows) issue(row + gridDim.x);
+        double2* orow = out + row * out_pitch;
+        if (MODE == 0) {
+            double2 e[8], o[8], mid;
+            fft_regs_half<LOGH>(v, u, at, xb, t1, t2, line_sync);
+            split_two_for_one<LOGH>(v, u, at, xb, e, o, line_sync, &mid);
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const int k = u + M1 * m;  // k < H/2
+                const double2 t = cmul(o[m], __ldg(tw + k));
+                __stcs(orow + k, cadd(e[m], t));                                  // X[k] = E + w^k O
+                const double2 d = csub(e[m], t);
+                if (k != 0) __stcs(orow + (H - k), make_double2(d.x, -d.y));       // X[H-k] = conj(E - w^k O)
+            }
+            if (u == 0) __stcs(orow + H / 2, make_double2(mid.x, -mid.y));         // X[H/2] = conj Z[H/2]
+        } else {
+#pragma unroll
+            for (int m = 0; m < 16; ++m) __stcs(orow + u + M1 * m, v[m]);
         }
     }
 }
@@ -594,6 +684,87 @@ static void check_x(int64_t nrows_full) {
     CK(cudaFree(t2));
 }
 
+
+template <typename T, int LOGN, int CTAS>
+static void check_xrow(int64_t nrows_full) {
+    constexpr int N = 1 << LOGN, H = N / 2;
+    using L = XRowLayout<T, LOGN>;
+    double2 *t1, *t2;
+    make_tables<LOGN - 1>(&t1, &t2);
+    std::vector<double2> htw(H / 2);
+    for (int k = 0; k < H / 2; ++k) {
+        const long double a = -6.283185307179586476925286766559005768L * k / N;
+        htw[k] = make_double2((double)cosl(a), (double)sinl(a));
+    }
+    double2* tw;
+    CK(cudaMalloc(&tw, sizeof(double2) * htw.size()));
+    CK(cudaMemcpy(tw, htw.data(), sizeof(double2) * htw.size(), cudaMemcpyHostToDevice));
+    const int64_t pitch = H;
+    auto run = [&](auto mode, const T* rho, const T* ux, const T* uy, const T* uz, int64_t nrows, double2** f) {
+        constexpr int MODE = decltype(mode)::value;
+        auto kern = k_xrow<T, LOGN, CTAS, MODE>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
+        const int grid = (int)std::min<int64_t>(nrows, (int64_t)g_sms * CTAS);
+        kern<<<grid, L::THREADS, L::total>>>(rho, ux, uy, uz, nrows, t1, t2, tw, f[0], f[1], f[2], pitch);
+        CK(cudaGetLastError());
+    };
+    for (int64_t nrows : {(int64_t)97, nrows_full}) {
+        if (nrows <= 0) continue;
+        const int64_t ne = nrows * N;
+        T *rho, *ux, *uy, *uz;
+        for (auto pp : {&rho, &ux, &uy, &uz}) CK(cudaMalloc(pp, sizeof(T) * ne));
+        k_fill_fields<T><<<4096, 256>>>(rho, ux, uy, uz, ne, 99);
+        double2* f[3];
+        for (auto& p : f) CK(cudaMalloc(&p, sizeof(double2) * nrows * pitch));
+        if (nrows == 97) {
+            run(std::integral_constant<int, 0>(), rho, ux, uy, uz, nrows, f);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { printf("CHECK xrow N %d: CUDA error %s\n", N, cudaGetErrorString(e)); exit(4); }
+            double* w;
+            double2* ref;
+            CK(cudaMalloc(&w, sizeof(double) * ne));
+            CK(cudaMalloc(&ref, sizeof(double2) * nrows * (N / 2 + 1)));
+            cufftHandle h;
+            int n[1] = {N};
+            if (cufftPlanMany(&h, 1, n, nullptr, 1, N, nullptr, 1, N / 2 + 1, CUFFT_D2Z, (int)nrows) != CUFFT_SUCCESS) exit(3);
+            const T* uu[3] = {ux, uy, uz};
+            std::vector<double2> h_ref(nrows * (N / 2 + 1)), h_out(nrows * pitch);
+            for (int c = 0; c < 3; ++c) {
+                k_weight_ref<T><<<256, 256>>>(rho, uu[c], w, ne);
+                if (cufftExecD2Z(h, w, (cufftDoubleComplex*)ref) != CUFFT_SUCCESS) exit(3);
+                CK(cudaDeviceSynchronize());
+                CK(cudaMemcpy(h_ref.data(), ref, sizeof(double2) * h_ref.size(), cudaMemcpyDeviceToHost));
+                CK(cudaMemcpy(h_out.data(), f[c], sizeof(double2) * h_out.size(), cudaMemcpyDeviceToHost));
+                double err = 0, mx = 0;
+                for (int64_t r = 0; r < nrows; ++r)
+                    for (int k = 0; k < N / 2; ++k) {
+                        const double2 a = h_out[r * pitch + k], b = h_ref[r * (N / 2 + 1) + k];
+                        err = std::max(err, std::max(fabs(a.x - b.x), fabs(a.y - b.y)));
+                        mx = std::max(mx, std::max(fabs(b.x), fabs(b.y)));
+                    }
+                printf("CHECK xrow %s N %d ctas %d smem %zu comp %d: rel err %.3e %s\n", sizeof(T) == 8 ? "f64" : "f32", N, CTAS,
+                       (size_t)L::total, c, err / mx, err / mx < 1e-13 ? "ok" : "FAIL");
+            }
+            cufftDestroy(h);
+            CK(cudaFree(w));
+            CK(cudaFree(ref));
+        } else {
+            CK(cudaDeviceSynchronize());
+            const double gb = (4.0 * sizeof(T) + 24.0) * (double)ne / 1e9;
+            float ms = time_ms([&] { run(std::integral_constant<int, 1>(), rho, ux, uy, uz, nrows, f); });
+            printf("TIME xrow %s N %d ctas %d copy-only %8.3f ms %7.1f GB/s\n", sizeof(T) == 8 ? "f64" : "f32", N, CTAS, ms, gb / (ms * 1e-3));
+            ms = time_ms([&] { run(std::integral_constant<int, 0>(), rho, ux, uy, uz, nrows, f); });
+            printf("TIME xrow %s N %d ctas %d fft       %8.3f ms %7.1f GB/s (algorithmic %0.1f GB)\n", sizeof(T) == 8 ? "f64" : "f32", N, CTAS,
+                   ms, gb / (ms * 1e-3), gb);
+            fflush(stdout);
+        }
+        for (auto p : {(void*)rho, (void*)ux, (void*)uy, (void*)uz, (void*)f[0], (void*)f[1], (void*)f[2]}) CK(cudaFree(p));
+    }
+    CK(cudaFree(t1));
+    CK(cudaFree(t2));
+    CK(cudaFree(tw));
+}
+
 static void time_cols(int64_t nfull, bool all) {
     constexpr int LOGN = 10, N = 1024;
     double2 *t1, *t2;
@@ -651,6 +822,19 @@ int main(int argc, char** argv) {
         run_tma<10, 0>(f[0], sz, t1, t2, Prune{2, kmax2, N});
         CK(cudaDeviceSynchronize());
         printf("PROF DONE\n");
+        return 0;
+    }
+    if (what == "xrow") {
+        check_xrow<double, 9, 4>(0);
+        check_xrow<float, 9, 4>(0);
+        check_xrow<double, 11, 2>(0);
+        check_xrow<float, 11, 2>(0);
+        check_xrow<float, 10, 4>(1024 * nfull);
+        check_xrow<double, 10, 4>(1024 * nfull);
+        check_xrow<double, 10, 3>(1024 * nfull);
+        check_xrow<double, 10, 2>(1024 * nfull);
+        check_x<double, 10, 1, 2>(1024 * nfull);
+        printf("LAB DONE\n");
         return 0;
     }
     if (what == "all" || what == "cols") {
