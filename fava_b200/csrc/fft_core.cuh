@@ -153,20 +153,50 @@ struct Owner {
     }
 };
 
-// twiddles after pass 1 (thread j, register q) and pass 2 (thread (q, j2), register q2)
+// twiddles after pass 1 (thread j, register q) and pass 2 (thread (q, j2), register q2): v[q] *= w^(j q).
+// Four table loads per pass (w^j, w^2j, w^4j, w^8j, each correctly rounded) and eleven products give the fifteen
+// factors: the loads of a full table row per factor were the top stall of the column kernels (long scoreboard) and
+// 15 % of the shared-memory / L1 wavefronts of the x pass, while the fp64 pipe sits below 30 %.  A factor is the
+// product of at most four rounded values (relative error < 5e-16).
+__device__ __forceinline__ void twiddle_powers(double2 (&v)[16], double2 w1, double2 w2, double2 w4, double2 w8) {
+    const double2 w3 = cmul(w1, w2), w5 = cmul(w4, w1), w6 = cmul(w4, w2), w7 = cmul(w4, w3);
+    v[1] = cmul(v[1], w1);
+    v[2] = cmul(v[2], w2);
+    v[3] = cmul(v[3], w3);
+    v[4] = cmul(v[4], w4);
+    v[5] = cmul(v[5], w5);
+    v[6] = cmul(v[6], w6);
+    v[7] = cmul(v[7], w7);
+    v[8] = cmul(v[8], w8);
+    v[9] = cmul(v[9], cmul(w8, w1));
+    v[10] = cmul(v[10], cmul(w8, w2));
+    v[11] = cmul(v[11], cmul(w8, w3));
+    v[12] = cmul(v[12], cmul(w8, w4));
+    v[13] = cmul(v[13], cmul(w8, w5));
+    v[14] = cmul(v[14], cmul(w8, w6));
+    v[15] = cmul(v[15], cmul(w8, w7));
+}
 template <int LOGN>
 __device__ __forceinline__ void twiddle1(double2 (&v)[16], int u, const double2* __restrict__ t1) {
     using P = RegPlan<LOGN>;
+#ifdef FAVA_TW_TABLE
 #pragma unroll
     for (int q = 1; q < 16; ++q) v[q] = cmul(v[q], __ldg(t1 + q * P::M1 + u));
+#else
+    twiddle_powers(v, __ldg(t1 + P::M1 + u), __ldg(t1 + 2 * P::M1 + u), __ldg(t1 + 4 * P::M1 + u), __ldg(t1 + 8 * P::M1 + u));
+#endif
 }
 template <int LOGN>
 __device__ __forceinline__ void twiddle2(double2 (&v)[16], int u, const double2* __restrict__ t2) {
     using P = RegPlan<LOGN>;
     if constexpr (P::M2 > 1) {
         const int j2 = u % P::M2;
+#ifdef FAVA_TW_TABLE
 #pragma unroll
         for (int q2 = 1; q2 < 16; ++q2) v[q2] = cmul(v[q2], __ldg(t2 + q2 * P::M2 + j2));
+#else
+        twiddle_powers(v, __ldg(t2 + P::M2 + j2), __ldg(t2 + 2 * P::M2 + j2), __ldg(t2 + 4 * P::M2 + j2), __ldg(t2 + 8 * P::M2 + j2));
+#endif
     }
 }
 

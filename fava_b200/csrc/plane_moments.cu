@@ -356,7 +356,8 @@ __global__ void k_finalize(const double* __restrict__ mom, const double* __restr
 // pass) and once by the warp that owns its ROW (y bins).
 //   work item = (z plane, strip of 256 columns); a persistent 512-thread CTA walks the item in tiles of 8 rows x 256
 //   columns x 4 fields, which arrive through 2-D tensor maps (cp.async.bulk.tensor.2d, one box per field) into a
-//   3-stage ring while earlier tiles are consumed;
+//   3-stage ring while earlier tiles are consumed; a 17th warp is the producer: it re-fills a stage as soon as the 16
+//   consumer warps have released it (full / empty mbarriers, no CTA-wide barrier in the loop, so the two groups drift);
 //   group A (256 threads): thread = column; 13 accumulators about the column's x pivot, kept in registers over the 128
 //   tiles of the item, one store of [13][256] partials per item -> k_reduce_partials / k_partials_to_planes;
 //   group B (8 warps): warp = row; lane l takes columns l, l+32, ... about the row's y pivot, then the 13 sums of the warp
@@ -364,8 +365,11 @@ __global__ void k_finalize(const double* __restrict__ mom, const double* __restr
 //   of its values and sends the other half) and lanes 0,2,..,24 store one 128-byte record per (z, strip, row)
 //   -> k_reduce_rows.  Fixed orders throughout: bitwise reproducible.
 // fp64 pipe ~55 %, shared-memory reads 64 B/cell, shuffles 4/cell: under the HBM time of 32 B/cell.
-constexpr int kXyzCols = 256, kXyzRows = 8, kXyzStages = 3, kXyzThreads = 512;
+constexpr int kXyzCols = 256, kXyzRows = 8, kXyzStages = 3, kXyzConsumers = 512, kXyzThreads = kXyzConsumers + 32;
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
@@ -396,46 +400,68 @@ __global__ void __launch_bounds__(kXyzThreads, 1)
     k_moments_xyz(const __grid_constant__ CUtensorMap tm_rho, const __grid_constant__ CUtensorMap tm_ux,
                   const __grid_constant__ CUtensorMap tm_uy, const __grid_constant__ CUtensorMap tm_uz, int nz, int ny, int nx,
                   const double* __restrict__ piv_x, const double* __restrict__ piv_y, double* __restrict__ xpartial,
-                  double* __restrict__ ypartial) {
+                  double* __restrict__ ypartial, unsigned long long* __restrict__ item_counter) {
     constexpr int TILE = kXyzRows * kXyzCols;  // cells of one field in a tile
     extern __shared__ __align__(1024) unsigned char xyz_smem[];
     T* ring = reinterpret_cast<T*>(xyz_smem);  // [stages][4][8][256]
     uint64_t* full = reinterpret_cast<uint64_t*>(xyz_smem + sizeof(T) * kXyzStages * 4 * TILE);
+    uint64_t* empty = full + kXyzStages;
+    long long* info = reinterpret_cast<long long*>(empty + kXyzStages);  // per stage: item * tpi + tile, -1 = no more work
     const int tid = threadIdx.x, lane = tid & 31;
     const bool colgroup = tid < kXyzCols;
     const int row = (tid - kXyzCols) >> 5;  // group B: the warp's row inside a tile
     const int nstrips = nx / kXyzCols, tpi = ny / kXyzRows;
     const int64_t nitems = (int64_t)nz * nstrips;
-    const int64_t my_items = blockIdx.x < nitems ? (nitems - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const int64_t total = my_items * tpi;
 
-    auto issue = [&](int64_t g) {  // one thread
-        const int64_t item = blockIdx.x + (g / tpi) * gridDim.x;
-        const int z = (int)(item / nstrips), strip = (int)(item - (int64_t)z * nstrips);
-        const int y0 = (int)(g % tpi) * kXyzRows;
-        const int s = (int)(g % kXyzStages);
-        T* dst = ring + (size_t)s * 4 * TILE;
-        mbar_expect_tx(&full[s], (unsigned)(sizeof(T) * 4 * TILE));
-        tma_load_2d(dst, &tm_rho, strip * kXyzCols, z * ny + y0, &full[s]);
-        tma_load_2d(dst + TILE, &tm_ux, strip * kXyzCols, z * ny + y0, &full[s]);
-        tma_load_2d(dst + 2 * TILE, &tm_uy, strip * kXyzCols, z * ny + y0, &full[s]);
-        tma_load_2d(dst + 3 * TILE, &tm_uz, strip * kXyzCols, z * ny + y0, &full[s]);
-    };
     if (tid == 0) {
-        for (int s = 0; s < kXyzStages; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < kXyzStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kXyzConsumers / 32);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         asm volatile("fence.proxy.async;\n" ::: "memory");
-        for (int64_t g = 0; g < kXyzStages && g < total; ++g) issue(g);
     }
     __syncthreads();
 
+    if (tid >= kXyzConsumers) {  // ---- producer warp: one lane feeds the ring ----
+        // items come from a global counter: a CTA that starts late (another kernel still holds its SM) takes fewer
+        if (lane == 0) {
+            int64_t g = 0;
+            for (;;) {
+                const int64_t item = (int64_t)atomicAdd(item_counter, 1ull);
+                if (item >= nitems) break;
+                const int z = (int)(item / nstrips), strip = (int)(item - (int64_t)z * nstrips);
+                for (int tile = 0; tile < tpi; ++tile, ++g) {
+                    const int s = (int)(g % kXyzStages);
+                    if (g >= kXyzStages) mbar_wait(&empty[s], (unsigned)(((g / kXyzStages) - 1) & 1));
+                    info[s] = item * tpi + tile;
+                    T* dst = ring + (size_t)s * 4 * TILE;
+                    const int y = z * ny + tile * kXyzRows;
+                    mbar_expect_tx(&full[s], (unsigned)(sizeof(T) * 4 * TILE));
+                    tma_load_2d(dst, &tm_rho, strip * kXyzCols, y, &full[s]);
+                    tma_load_2d(dst + TILE, &tm_ux, strip * kXyzCols, y, &full[s]);
+                    tma_load_2d(dst + 2 * TILE, &tm_uy, strip * kXyzCols, y, &full[s]);
+                    tma_load_2d(dst + 3 * TILE, &tm_uz, strip * kXyzCols, y, &full[s]);
+                }
+            }
+            const int s = (int)(g % kXyzStages);  // end marker: completes the stage's phase without a copy
+            if (g >= kXyzStages) mbar_wait(&empty[s], (unsigned)(((g / kXyzStages) - 1) & 1));
+            info[s] = -1;
+            mbar_arrive(&full[s]);
+        }
+        return;
+    }
+
     Acc<kNM> ax;
     double cx0 = 0.0, cx1 = 0.0, cx2 = 0.0;
-    for (int64_t g = 0; g < total; ++g) {
-        const int64_t item = blockIdx.x + (g / tpi) * gridDim.x;
-        const int z = (int)(item / nstrips), strip = (int)(item - (int64_t)z * nstrips);
-        const int tile = (int)(g % tpi), y0 = tile * kXyzRows;
+    for (int64_t g = 0;; ++g) {
         const int s = (int)(g % kXyzStages);
+        mbar_wait(&full[s], (unsigned)((g / kXyzStages) & 1));
+        const long long code = info[s];
+        if (code < 0) break;
+        const int64_t item = code / tpi;
+        const int z = (int)(item / nstrips), strip = (int)(item - (int64_t)z * nstrips);
+        const int tile = (int)(code - item * tpi), y0 = tile * kXyzRows;
         const T* st = ring + (size_t)s * 4 * TILE;
         if (colgroup && tile == 0) {
             ax.clear();
@@ -444,13 +470,14 @@ __global__ void __launch_bounds__(kXyzThreads, 1)
         }
         double cy0 = 0.0, cy1 = 0.0, cy2 = 0.0;
         if (!colgroup) cy0 = piv_y[y0 + row], cy1 = piv_y[ny + y0 + row], cy2 = piv_y[2 * ny + y0 + row];
-        mbar_wait(&full[s], (unsigned)((g / kXyzStages) & 1));
         if (colgroup) {
 #pragma unroll
             for (int r = 0; r < kXyzRows; ++r) {
                 const int o = r * kXyzCols + tid;
                 ax.add((double)st[o], (double)st[TILE + o], (double)st[2 * TILE + o], (double)st[3 * TILE + o], cx0, cx1, cx2);
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);  // this warp has read everything it needs from the stage
             if (tile == tpi - 1) {
                 double* out = xpartial + (int64_t)z * kNM * nx + (int64_t)strip * kXyzCols + tid;
 #pragma unroll
@@ -464,6 +491,8 @@ __global__ void __launch_bounds__(kXyzThreads, 1)
                 const int o = row * kXyzCols + lane + 32 * j;
                 ay.add((double)st[o], (double)st[TILE + o], (double)st[2 * TILE + o], (double)st[3 * TILE + o], cy0, cy1, cy2);
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
             double v[16];
 #pragma unroll
             for (int m = 0; m < 16; ++m) v[m] = m < kNM ? ay.m[m] : 0.0;
@@ -472,8 +501,6 @@ __global__ void __launch_bounds__(kXyzThreads, 1)
             if ((lane & 1) == 0 && m < kNM)
                 ypartial[((((int64_t)z * nstrips + strip) * ny) + y0 + row) * 16 + m] = tot;
         }
-        __syncthreads();  // every thread is done with stage s
-        if (tid == 0 && g + kXyzStages < total) issue(g + kXyzStages);
     }
 }
 
@@ -639,12 +666,15 @@ static int launch_xyz(fava_ctx* ctx, const T* rho, const T* ux, const T* uy, con
         rc = ctx_tensor_map(ctx, src[f], dt, 2, dims, strides, box, &tm[f]);
         if (rc) return rc;
     }
-    const size_t smem = sizeof(T) * kXyzStages * 4 * kXyzRows * kXyzCols + 64;
+    const size_t smem = sizeof(T) * kXyzStages * 4 * kXyzRows * kXyzCols + 24 * kXyzStages;
     auto kern = k_moments_xyz<T>;
     FAVA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = (unsigned)std::min<int64_t>(nz * nstrips, ctx->num_sms);
+    if (!ctx->tile_counters) FAVA_CHECK_CUDA(cudaMalloc(&ctx->tile_counters, sizeof(unsigned long long) * 64));
+    unsigned long long* counter = (unsigned long long*)ctx->tile_counters + (ctx->tile_counter_next++ & 63);
+    FAVA_CHECK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
     kern<<<grid, kXyzThreads, smem, st>>>(tm[0], tm[1], tm[2], tm[3], (int)nz, (int)ny, (int)nx, piv_x, piv_y, (double*)wx,
-                                         (double*)wy);
+                                         (double*)wy, counter);
     FAVA_LAUNCHED();
     const int64_t n = (int64_t)FAVA_NMOM * nx;
     k_reduce_partials<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>((const double*)wx, (int)nz, nx, kNM, FAVA_NMOM, mom_x, 0,
