@@ -280,7 +280,8 @@ def test_data_returns_reference_layout(fava, tmp_path):
     assert m.data("no such field") is None
 
 
-@pytest.mark.parametrize("n,dtype", [(256, np.float64), (256, np.float32), (512, np.float32)])
+@pytest.mark.parametrize("n,dtype", [(256, np.float64), (256, np.float32), (512, np.float32), (512, np.float64), (1024, np.float64),
+                                     (2048, np.float32)])
 def test_hand_written_transform_matches_torch_fft(cuda_device, n, dtype):
     """Power-of-two grids take the hand-written passes (csrc/fft.cu): the fused weighting + x pass, the y pass and the
     pruned z pass, each compared with torch.fft (cuFFT, test reference only) on the elements a bin can read."""
