@@ -184,7 +184,8 @@ KERNEL_NAMES = {
     "plane_moments_xyz": "k_moments_xyz (fava_plane_moments_xyz: x, y AND z profiles from one 32 B/cell read, TMA tensor tiles)",
     "plane_moments_xz": "k_moments_cols + k_partials_to_planes (fava_plane_moments_xz: x AND z profiles from one read)",
     "plane_moments_axis1": "k_moments_rows (fava_plane_moments, axis y)",
-    "transform_x": "k_fft_x_weight (fava_ke_transform_x: sqrt(rho) u weighting fused with the x transform, TMA-fed)",
+    "transform_x": "k_fft_x_row (fava_ke_transform_x: sqrt(rho) u weighting fused with the x transform; one row per CTA as a "
+                   "half-length complex line in registers, rows fed by TMA bulk copies)",
     "transform_y": "k_fft_cols<.,1> (fava_ke_transform_y: in-place y transform, TMA tensor tiles, pruned outputs)",
     "transform_z": "k_fft_cols<.,2> (fava_ke_transform_z: in-place z transform, pruned to the spectral sphere)",
     "spectrum_bin": "k_spectrum_bin (fava_spectrum_bin)",

@@ -106,7 +106,7 @@ struct BinTile {
     int neg;          // 1: kz = -(32 b + i), else kz = 32 b + i
 };
 
-__global__ void __launch_bounds__(kBinT, 2)
+__global__ void __launch_bounds__(kBinT, 3)
     k_spectrum_bin(const double2* __restrict__ fx, const double2* __restrict__ fy, const double2* __restrict__ fz,
                    BinParams p, double* __restrict__ partial) {
     extern __shared__ __align__(16) unsigned char dyn_raw[];
@@ -178,44 +178,55 @@ __global__ void __launch_bounds__(kBinT, 2)
         __syncthreads();
 
         // ---- phase C: projection, shell index, warp-level segmented reduction ---------------------------
+        // two rows at a time: their scans are independent dependency chains (shuffle -> add, five rounds) and interleave
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int ib = warp + kBinWarps * i;
-            const int q = b0 + ib;
-            int key = -1;
-            double vt = 0.0, vl = 0.0, vc = 0.0;
-            if (kx < nh && q < nh && !(T.neg && q == 0)) {
-                const int kz = T.neg ? -q : q;
-                const int k2 = kx * kx + T.ky * T.ky + kz * kz;
-                if (k2 <= p.kmax2) {
-                    const double sgn = T.neg ? -1.0 : 1.0;  // conjugate of the folded half
-                    const double2 t0 = S[0][lane][ib], t1 = S[1][lane][ib], t2 = S[2][lane][ib];
-                    const double lre = fma((double)kx, t0.x, fma((double)T.ky, t1.x, (double)kz * t2.x));
-                    const double lim = sgn * fma((double)kx, t0.y, fma((double)T.ky, t1.y, (double)kz * t2.y));
-                    key = shell_of(k2);
-                    const double w = kx == 0 ? 1.0 : 2.0;
-                    vt = w * 0.5 * tot[i] * p.norm2;
-                    vl = k2 > 0 ? w * (lre * lre + lim * lim) / (double)k2 * p.norm2 : 0.0;
-                    vc = w;
+        for (int ip = 0; ip < 4; ip += 2) {
+            int key[2];
+            double vt[2], vl[2];
+            unsigned seg[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int i = ip + h;
+                const int ib = warp + kBinWarps * i;
+                const int q = b0 + ib;
+                key[h] = -1, vt[h] = 0.0, vl[h] = 0.0;
+                if (kx < nh && q < nh && !(T.neg && q == 0)) {
+                    const int kz = T.neg ? -q : q;
+                    const int k2 = kx * kx + T.ky * T.ky + kz * kz;
+                    if (k2 <= p.kmax2) {
+                        const double sgn = T.neg ? -1.0 : 1.0;  // conjugate of the folded half
+                        const double2 t0 = S[0][lane][ib], t1 = S[1][lane][ib], t2 = S[2][lane][ib];
+                        const double lre = fma((double)kx, t0.x, fma((double)T.ky, t1.x, (double)kz * t2.x));
+                        const double lim = sgn * fma((double)kx, t0.y, fma((double)T.ky, t1.y, (double)kz * t2.y));
+                        key[h] = shell_of(k2);
+                        const double w = kx == 0 ? 1.0 : 2.0;
+                        vt[h] = w * 0.5 * tot[i] * p.norm2;
+                        vl[h] = k2 > 0 ? w * (lre * lre + lim * lim) / (double)k2 * p.norm2 : 0.0;
+                    }
                 }
+                // lanes with my shell form one contiguous run (|k| grows with kx): its lane mask replaces the key exchange
+                // of the segmented scan, marks the tail, and gives the point count of the run without summing it
+                seg[h] = __match_any_sync(0xffffffffu, key[h]);
             }
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
-                const int ko = __shfl_up_sync(0xffffffffu, key, d);
-                const double to = __shfl_up_sync(0xffffffffu, vt, d);
-                const double lo = __shfl_up_sync(0xffffffffu, vl, d);
-                const double co = __shfl_up_sync(0xffffffffu, vc, d);
-                if (lane >= d && ko == key) vt += to, vl += lo, vc += co;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const double to = __shfl_up_sync(0xffffffffu, vt[h], d);
+                    const double lo = __shfl_up_sync(0xffffffffu, vl[h], d);
+                    if (lane >= d && ((seg[h] >> (lane - d)) & 1u)) vt[h] += to, vl[h] += lo;
+                }
             }
-            const int kn = __shfl_down_sync(0xffffffffu, key, 1);
-            const bool tail = (lane == 31) || (kn != key);
-            if (tail && key >= 0) {
-                const int s = min(key - mlo, kSlots - 1);
-                wb_tot[warp][s] += vt;
-                wb_lon[warp][s] += vl;
-                wb_cnt[warp][s] += vc;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (key[h] >= 0 && lane == 31 - __clz(seg[h])) {  // tail of the run
+                    const int s = min(key[h] - mlo, kSlots - 1);
+                    wb_tot[warp][s] += vt[h];
+                    wb_lon[warp][s] += vl[h];
+                    wb_cnt[warp][s] += 2.0 * __popc(seg[h]) - ((a0 == 0 && (seg[h] & 1u)) ? 1.0 : 0.0);  // weight 1 at kx = 0
+                }
+                __syncwarp();  // two rows of a warp may end runs in the same slot
             }
-            __syncwarp();
         }
         __syncthreads();  // tiles consumed, warp bins complete
         if (t < kSlots) {
@@ -246,35 +257,29 @@ __global__ void __launch_bounds__(kBinT, 2)
         const int jm = (n - j) % n;
         const int jml = p.local_of_ky ? p.local_of_ky[jm] : jm;
         const bool self = jm == j;  // ky = 0
-        BinTile T;
-        T.jl = jl, T.jml = jml, T.ky = ky, T.a = a, T.b = b, T.neg = 0;
-        process(T);  // M1: plane +ky, (A, +B)
+        // the members of the group in the order that makes one member's direct operand the next one's transposed operand;
+        // ONE copy of the tile code walks the list (inlined eight times it was 11 k instructions and the kernel stalled
+        // on instruction fetch: ncu no_instruction 1.2 per issue)
+        BinTile list[8];
+        int nt = 0;
+        auto push = [&](int jl_, int jml_, int ky_, int a_, int b_, int neg_) {
+            list[nt].jl = jl_, list[nt].jml = jml_, list[nt].ky = ky_, list[nt].a = a_, list[nt].b = b_, list[nt].neg = neg_;
+            ++nt;
+        };
+        push(jl, jml, ky, a, b, 0);                         // M1: plane +ky, (A, +B)
+        if (a != b) push(jl, jml, ky, b, a, 0);             // M2: plane +ky, (B, +A)
+        push(jl, jml, ky, a, b, 1);                         // M3: plane +ky, (A, -B)
+        if (!self) push(jml, jl, -ky, b, a, 1);             // M4: plane -ky, (B, -A): its operands are M3's, swapped
         if (a != b) {
-            T.a = b, T.b = a;
-            process(T);  // M2: plane +ky, (B, +A)
-        }
-        T.a = a, T.b = b, T.neg = 1;
-        process(T);  // M3: plane +ky, (A, -B)
-        if (!self) {
-            T.jl = jml, T.jml = jl, T.ky = -ky, T.a = b, T.b = a;
-            process(T);  // M4: plane -ky, (B, -A): its operands are M3's, swapped
-        }
-        if (a != b) {
-            T.jl = jl, T.jml = jml, T.ky = ky, T.a = b, T.b = a;
-            process(T);  // M5: plane +ky, (B, -A)
-            if (!self) {
-                T.jl = jml, T.jml = jl, T.ky = -ky, T.a = a, T.b = b;
-                process(T);  // M6: plane -ky, (A, -B)
-            }
+            push(jl, jml, ky, b, a, 1);                     // M5: plane +ky, (B, -A)
+            if (!self) push(jml, jl, -ky, a, b, 1);         // M6: plane -ky, (A, -B)
         }  // a == b: M4 already covered plane -ky, (A, -A)
         if (!self) {
-            T.jl = jml, T.jml = jl, T.ky = -ky, T.neg = 0, T.a = a, T.b = b;
-            process(T);  // M7: plane -ky, (A, +B)
-            if (a != b) {
-                T.a = b, T.b = a;
-                process(T);  // M8: plane -ky, (B, +A)
-            }
+            push(jml, jl, -ky, a, b, 0);                    // M7: plane -ky, (A, +B)
+            if (a != b) push(jml, jl, -ky, b, a, 0);        // M8: plane -ky, (B, +A)
         }
+#pragma unroll 1
+        for (int i = 0; i < nt; ++i) process(list[i]);
     }
     __syncthreads();
     double* out = partial + (int64_t)blockIdx.x * 3 * p.nbins;
@@ -446,9 +451,10 @@ int fava_spectrum_bin(fava_ctx* ctx, const double* d_fx, const double* d_fy, con
     p.norm2 = norm * norm;
     const size_t nb_pad = (size_t)((3 * p.nbins + 1) & ~1);
     const size_t dyn = sizeof(double) * (nb_pad + 3 * kBinWarps * kSlots) + 3 * sizeof(double2) * kTS * (kTS + 1);
-    // two CTAs per SM; a third one (80 registers, 72 KB: it fits) measured 6 % slower at 1024^3 - more groups in flight
-    // evict each other's paired tiles from L2 before their second use
-    const int ncta = (int)std::min<int64_t>(p.ngroups, (int64_t)ctx->num_sms * 2);
+    // three CTAs per SM (80 registers, 72 KB of shared memory at n = 1024).  Measured at 1024^3: with the tile code inlined
+    // once per group member (11 k instructions, instruction-fetch stalls) 2 CTAs/SM took 6.1 ms and 3 took 6.5; with ONE
+    // copy walked over the member list 2 / 3 CTAs per SM take 6.4 / 5.4 ms.
+    const int ncta = (int)std::min<int64_t>(p.ngroups, (int64_t)ctx->num_sms * 3);
     void* ws;
     rc = ctx_workspace(ctx, WS_PARTIALS, sizeof(double) * 3 * (size_t)p.nbins * ncta, &ws);
     if (rc) return rc;
