@@ -397,3 +397,56 @@ def test_reynolds_time_series_over_plt_files(fava, tmp_path):
         _, s0, m0 = orc.reynolds_stress(geom, oracle_data(fulls[i]), axis=0)
         for k in STRESS:
             maxnorm_close(stress[k], s0[k], RTOL, f"file {i} {k}")
+
+
+@pytest.mark.parametrize("n", [256, 1024])
+def test_y_pass_fused_with_the_exchange_on_one_gpu(cuda_device, n):
+    """fava_fft_y_scatter (the y pass whose output rows go straight into the owners' receive buffers) with this GPU
+    playing every rank: two 'ranks' own interleaved ky sets in permuted row order, the Nyquist row has no owner; chunked
+    calls (z_offset) fill the same buffers as one call.  Checked against torch.fft on the rows the pass must write."""
+    import torch
+
+    from fava_b200 import device
+
+    nz, pitch = 8, n // 2
+    g = torch.Generator(device=cuda_device)
+    g.manual_seed(n + 1)
+    src = (torch.randn((nz, n, pitch), generator=g, device=cuda_device, dtype=torch.float64)
+           + 1j * torch.randn((nz, n, pitch), generator=g, device=cuda_device, dtype=torch.float64))
+    ref = torch.fft.fft(src, dim=1)
+    ky = np.arange(n)
+    owner = (ky % 2).astype(np.int32)
+    owner[n // 2] = -1
+    nyl = n // 2
+    row = np.zeros(n, dtype=np.int32)
+    for r in (0, 1):
+        mine = ky[(owner == r)]
+        row[mine] = np.arange(mine.size)[::-1]  # permuted: the kernel must go through the table
+    me, nz_local = 1, nz  # this GPU acts as rank 1 of 2: its planes land at z slots [nz_local, 2 nz_local)
+    recv = [torch.zeros((2 * nz_local, nyl, pitch), dtype=torch.complex128, device=cuda_device) for _ in range(2)]
+    peers = torch.tensor([t.data_ptr() for t in recv], dtype=torch.int64, device=cuda_device)
+    t_owner, t_row = torch.from_numpy(owner).to(cuda_device), torch.from_numpy(row).to(cuda_device)
+    work = src.clone()
+    device.fft_y_scatter(work.data_ptr(), n, nz, peers, t_owner, t_row, me, nz_local, nyl, max_ctas=40)
+    kmax2 = n * n // 4 - 3 * n // 2 + 2
+    wn = np.where(ky < n // 2, ky, ky - n)
+    kx0 = (np.arange(pitch) // (8192 // n)) * (8192 // n)
+    keep = torch.from_numpy((wn[:, None] ** 2 + kx0[None, :] ** 2) <= kmax2).to(cuda_device)
+    for r in (0, 1):
+        mine = torch.from_numpy(ky[owner == r]).to(cuda_device)
+        rows = torch.from_numpy(row[ky[owner == r]].astype(np.int64)).to(cuda_device)
+        got = recv[r][me * nz_local:(me + 1) * nz_local][:, rows, :]
+        want = ref[:, mine, :]
+        m = keep[mine][None]
+        maxnorm_close(torch.view_as_real(torch.where(m, got, torch.zeros_like(got))).cpu().numpy(),
+                      torch.view_as_real(torch.where(m, want, torch.zeros_like(want))).cpu().numpy(), 1e-13, f"rank {r}")
+        assert float(recv[r][:me * nz_local].abs().max()) == 0.0  # nobody else's z slots were touched
+    # the same slab in two chunks (as stats.host_step feeds it) fills the same buffers bit for bit
+    again = [torch.zeros_like(t) for t in recv]
+    peers2 = torch.tensor([t.data_ptr() for t in again], dtype=torch.int64, device=cuda_device)
+    work = src.clone()
+    half = nz // 2
+    device.fft_y_scatter(work.data_ptr(), n, half, peers2, t_owner, t_row, me, nz_local, nyl, z_offset=0)
+    device.fft_y_scatter(work.data_ptr() + half * n * pitch * 16, n, nz - half, peers2, t_owner, t_row, me, nz_local, nyl, z_offset=half)
+    for r in (0, 1):
+        assert torch.equal(torch.view_as_real(again[r]), torch.view_as_real(recv[r]))
