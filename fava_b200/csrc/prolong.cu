@@ -58,6 +58,36 @@ __global__ void __launch_bounds__(256)
         const int nrows = wy * wz;
         int iy = row0 % wy, iz = row0 / wy;  // once per tile; rows then advance by increments
         const int dy = rows_per_iter % wy, dz = rows_per_iter / wy;
+        const bool whole = vec && wx == 2 * tpr;  // unclipped tile, one 16-byte pair per thread and row: the common case
+        if (whole) {
+            // four rows per step: the four source loads are in flight together, then four 16-byte streaming stores
+            const int x = xa + 2 * lane_x;
+            const int i0 = (x - d.off[0]) >> d.shift, i1 = (x + 1 - d.off[0]) >> d.shift;
+            for (int r = row0; r < nrows; r += 4 * rows_per_iter) {
+                double2 v[4];
+                double* dst[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    dst[k] = nullptr;
+                    if (r + k * rows_per_iter < nrows) {
+                        const int Y = ya + iy, Z = za + iz;
+                        dst[k] = out + ((int64_t)Z * g.NY + Y) * g.NX + x;
+                        if (d.block < 0) {
+                            v[k] = make_double2(0.0, 0.0);
+                        } else {
+                            const T* srow = src + (((Z - d.off[2]) >> d.shift) * g.nyb + ((Y - d.off[1]) >> d.shift)) * g.nxb;
+                            v[k] = make_double2((double)srow[i0], (double)srow[i1]);
+                        }
+                        iy += dy, iz += dz;
+                        if (iy >= wy) iy -= wy, ++iz;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (dst[k]) __stcs(reinterpret_cast<double2*>(dst[k]), v[k]);
+            }
+            continue;
+        }
         for (int r = row0; r < nrows; r += rows_per_iter) {
             const int Y = ya + iy, Z = za + iz;
             double* orow = out + ((int64_t)Z * g.NY + Y) * g.NX;

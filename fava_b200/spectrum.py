@@ -42,7 +42,8 @@ def exchange_ctas(world: int, num_sms: int = 148) -> int:
     run the plane-profile kernels, the completion tokens (NCCL needs an SM of its own) and the z passes of earlier
     components at the same time; the column kernels take their tiles from a counter, so sharing the GPU costs them no
     tail.  Measured at 2 GPUs with every SM given to the exchange: tokens and profile kernels queued behind it and the
-    step was serial (26.4 ms against 23.3 ms for half the single-GPU time)."""
+    step was serial (26.4 ms against 23.3 ms for half the single-GPU time); at 8 GPUs 64 / 80 / 100 CTAs all need 1.14 ms
+    per component (645 GB/s on the wire: the link is the bound) and the step takes 6.52 / 6.71 / 6.76 ms."""
     want = int(np.ceil(1.05 * 770.0 / (14.5 * (world - 1) / world)))
     return min(want, num_sms - 16)
 
