@@ -122,6 +122,8 @@ __global__ void __launch_bounds__(kBinT, 3)
     double(*wb_lon)[kSlots] = reinterpret_cast<double(*)[kSlots]>(wb + kBinWarps * kSlots);
     double(*wb_cnt)[kSlots] = reinterpret_cast<double(*)[kSlots]>(wb + 2 * kBinWarps * kSlots);
 
+    __shared__ BinTile list[8];
+    __shared__ int list_n;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     for (int i = t; i < 3 * p.nbins; i += kBinT) dyn[i] = 0.0;
     for (int i = t; i < 3 * kBinWarps * kSlots; i += kBinT) wb[i] = 0.0;
@@ -144,7 +146,8 @@ __global__ void __launch_bounds__(kBinT, 3)
             for (int i = 0; i < 4; ++i) {
                 const int ia = warp + kBinWarps * i;
                 const int kxa = a0 + ia;
-                const bool ok = qok && kxa < nh;
+                // only elements inside the sphere are fetched (zero-filled otherwise): tiles on the surface load no more than they use
+                const bool ok = qok && kxa < nh && kxa * kxa + T.ky * T.ky + q * q <= p.kmax2;
                 int64_t off = 0;
                 if (ok) off = T.neg ? (int64_t)((n - kxa) % n) * p.zstride + (int64_t)T.jml * p.pitch + q
                                     : (int64_t)kxa * p.zstride + (int64_t)T.jl * p.pitch + q;
@@ -161,7 +164,7 @@ __global__ void __launch_bounds__(kBinT, 3)
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int q = b0 + warp + kBinWarps * i;
-                const bool ok = kx < nh && q < nh && !(T.neg && q == 0);
+                const bool ok = kx < nh && q < nh && !(T.neg && q == 0) && kx * kx + T.ky * T.ky + q * q <= p.kmax2;
                 const int l = T.neg ? n - q : q;
                 const int64_t off = ok ? (int64_t)l * p.zstride + (int64_t)T.jl * p.pitch + kx : 0;
 #pragma unroll
@@ -260,26 +263,33 @@ __global__ void __launch_bounds__(kBinT, 3)
         // the members of the group in the order that makes one member's direct operand the next one's transposed operand;
         // ONE copy of the tile code walks the list (inlined eight times it was 11 k instructions and the kernel stalled
         // on instruction fetch: ncu no_instruction 1.2 per issue)
-        BinTile list[8];
-        int nt = 0;
-        auto push = [&](int jl_, int jml_, int ky_, int a_, int b_, int neg_) {
-            list[nt].jl = jl_, list[nt].jml = jml_, list[nt].ky = ky_, list[nt].a = a_, list[nt].b = b_, list[nt].neg = neg_;
-            ++nt;
-        };
-        push(jl, jml, ky, a, b, 0);                         // M1: plane +ky, (A, +B)
-        if (a != b) push(jl, jml, ky, b, a, 0);             // M2: plane +ky, (B, +A)
-        push(jl, jml, ky, a, b, 1);                         // M3: plane +ky, (A, -B)
-        if (!self) push(jml, jl, -ky, b, a, 1);             // M4: plane -ky, (B, -A): its operands are M3's, swapped
-        if (a != b) {
-            push(jl, jml, ky, b, a, 1);                     // M5: plane +ky, (B, -A)
-            if (!self) push(jml, jl, -ky, a, b, 1);         // M6: plane -ky, (A, -B)
-        }  // a == b: M4 already covered plane -ky, (A, -A)
-        if (!self) {
-            push(jml, jl, -ky, a, b, 0);                    // M7: plane -ky, (A, +B)
-            if (a != b) push(jml, jl, -ky, b, a, 0);        // M8: plane -ky, (B, +A)
+        // (the list lives in shared memory, written by one thread: as a per-thread array it went to local memory and
+        // cost 1.6 GB of DRAM writes per launch at 1024^3)
+        if (t == 0) {
+            int nt = 0;
+            auto push = [&](int jl_, int jml_, int ky_, int a_, int b_, int neg_) {
+                list[nt].jl = jl_, list[nt].jml = jml_, list[nt].ky = ky_, list[nt].a = a_, list[nt].b = b_, list[nt].neg = neg_;
+                ++nt;
+            };
+            push(jl, jml, ky, a, b, 0);                         // M1: plane +ky, (A, +B)
+            if (a != b) push(jl, jml, ky, b, a, 0);             // M2: plane +ky, (B, +A)
+            push(jl, jml, ky, a, b, 1);                         // M3: plane +ky, (A, -B)
+            if (!self) push(jml, jl, -ky, b, a, 1);             // M4: plane -ky, (B, -A): its operands are M3's, swapped
+            if (a != b) {
+                push(jl, jml, ky, b, a, 1);                     // M5: plane +ky, (B, -A)
+                if (!self) push(jml, jl, -ky, a, b, 1);         // M6: plane -ky, (A, -B)
+            }  // a == b: M4 already covered plane -ky, (A, -A)
+            if (!self) {
+                push(jml, jl, -ky, a, b, 0);                    // M7: plane -ky, (A, +B)
+                if (a != b) push(jml, jl, -ky, b, a, 0);        // M8: plane -ky, (B, +A)
+            }
+            list_n = nt;
         }
+        __syncthreads();  // also orders the previous group's last bin merge before this group's first tile
+        const int nt = list_n;
 #pragma unroll 1
         for (int i = 0; i < nt; ++i) process(list[i]);
+        __syncthreads();  // the list is free for the next group
     }
     __syncthreads();
     double* out = partial + (int64_t)blockIdx.x * 3 * p.nbins;
