@@ -135,7 +135,7 @@ def _plan(n: int, rank: int, world: int, dev) -> SlabPlan:
     return _plans[key]
 
 
-def exchange(p: SlabPlan, c: int, z_offset: int = 0, nz_chunk: int | None = None) -> None:
+def exchange(p: SlabPlan, c: int, z_offset: int = 0, nz_chunk: int | None = None, y_done: bool = False) -> None:
     """Stage 2 + slab -> ky-pencil exchange of component c on the current stream.
     Hand-written path: ONE kernel - the y pass of planes [z_offset, z_offset + nz_chunk) stores every output row straight
     into its owner's peer-mapped receive buffer over NVLink (fava_fft_y_scatter), so the transfer overlaps the transform
@@ -150,7 +150,8 @@ def exchange(p: SlabPlan, c: int, z_offset: int = 0, nz_chunk: int | None = None
     else:
         if z_offset or nz_chunk != p.nzl:
             raise ValueError("the cuFFT path exchanges whole slabs")
-        device.ke_transform_y(p.send[c], p.nzl, p.n, p.dev)
+        if not y_done:  # (stats.host_step has transformed the slab chunk by chunk already)
+            device.ke_transform_y(p.send[c], p.nzl, p.n, p.dev)
         device.a2a_pack(p.send[c], p.peer_tables[c], p.ky_of_dest, p.rank, p.world, p.nzl, p.n, p.nyl)
 
 
@@ -209,8 +210,11 @@ def slab_ke_spectrum(rho, ux, uy, uz, n: int, overlap=None, epilogue=None, xy_do
         p.ev_xy[c].record(cur)  # (hand-written path: marks the end of the x pass; the y pass is part of the exchange)
         with torch.cuda.stream(p.comm_stream):
             p.comm_stream.wait_event(p.ev_xy[c])
-            if not xy_done:  # else the rows were scattered chunk by chunk as the slab arrived (stats.host_step)
+            if not xy_done:
                 exchange(p, c)
+            elif not p.native:  # stats.host_step on the cuFFT path: 2-D transforms done chunk by chunk, rows still here
+                exchange(p, c, y_done=True)
+            # (hand-written path: stats.host_step scattered the rows chunk by chunk as the slab arrived)
             p.ev_packed[c].record(p.comm_stream)
         with torch.cuda.stream(p.token_stream):
             # every rank's stores of component c into my receive buffer are complete once all ranks have

@@ -163,9 +163,6 @@ def host_step(host, n: int, cell_volume: float, layer_volume: float, axes=(0, 1,
 
     w = spec.spectral_buffers(n, nzl, dev) if spectrum else None
     plan = spec._plan(n, dist.rank(), dist.world_size(), dev) if spectrum and dist.world_size() > 1 else None
-    if plan is not None and not plan.native:
-        raise NotImplementedError("host_step on several ranks needs a power-of-two grid in [256, 2048] (the cuFFT path "
-                                  "exchanges whole slabs: copy the slab to the device and use slab_step)")
     plane_bytes = device.spectral_bytes(n, 1) if spectrum else 0  # one z-plane of a spectral buffer: complex [n][pitch]
     mom, piv = {}, {}
     for (a, b), ev in zip(chunks, landed):
@@ -185,7 +182,7 @@ def host_step(host, n: int, cell_volume: float, layer_volume: float, axes=(0, 1,
                 mom[ax][:, a:b] = m
                 piv[ax][:, a:b] = pv
         if spectrum:
-            if plan is None:
+            if plan is None or not plan.native:  # (cuFFT path on several ranks: the rows are exchanged after the last chunk)
                 device.ke_transform_xy(*part, *[p + a * plane_bytes for p in w])
             else:  # several ranks: x pass of the chunk, then its y pass scatters the rows to their owners
                 device.ke_transform_x(*part, *[p + a * plane_bytes for p in w])

@@ -60,6 +60,11 @@ def main():
     many2 = spectrum.slab_ke_spectrum(*[t[a2:b2].contiguous() for t in tf2], n2)
     for k in one2:
         close(many2[k], one2[k], 1e-13, f"slab spectrum {k} (second grid size)")
+    # ... and streamed from the host on that grid size too (cuFFT path: the rows are exchanged after the last chunk)
+    host2 = [t[a2:b2].contiguous().cpu().pin_memory() for t in tf2]
+    hs2 = stats.host_step(host2, n2, 1.0 / n2**3, 1.0 / n2, chunk_planes=max(1, (b2 - a2) // 2))
+    for k in one2:
+        close(hs2["spectrum"][k], one2[k], 1e-13, f"host_step spectrum {k} (second grid size)")
     step = stats.slab_step(*ts, n, cv, lv)
     for k in one:
         close(step["spectrum"][k], one[k], 1e-13, f"slab_step spectrum {k}")
