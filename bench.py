@@ -252,7 +252,7 @@ def run_ours(args) -> dict:
                 with timer.bracket("transform_z"):
                     device.ke_transform_z(w[c], n, n, None, dev)
             with timer.bracket("spectrum_bin"):
-                device.spectrum_bin(w[0], w[1], w[2], n, n, None, None, sums)
+                device.spectrum_bin(w[0], w[1], w[2], n, n, None, sums)
         else:
             p = spectrum._plan(n, rank, world, dev)
             with timer.bracket("transform_x"):
@@ -265,7 +265,7 @@ def run_ours(args) -> dict:
                 with timer.bracket("transform_z"):
                     device.ke_transform_z(p.recv[c], n, p.nyl, p.ky_of_local, dev)
             with timer.bracket("spectrum_bin"):
-                device.spectrum_bin(p.recv[0], p.recv[1], p.recv[2], n, p.nyl, p.ky_of_local, p.local_of_ky, p.sums)
+                device.spectrum_bin(p.recv[0], p.recv[1], p.recv[2], n, p.nyl, p.ky_of_local, p.sums)
             dist.allreduce_sum_(p.sums)
 
     for _ in range(args.warmup):

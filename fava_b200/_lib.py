@@ -127,7 +127,7 @@ SIGNATURES: dict[str, tuple] = {
     ),
     "fava_spectrum_bin": (
         c_int,
-        [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_void_p, c_double, c_void_p, c_void_p],
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_double, c_void_p, c_void_p],
     ),
     "fava_spectrum_finalize": (
         c_int,
@@ -156,7 +156,7 @@ SIGNATURES: dict[str, tuple] = {
     "fava_ipc_close": (c_int, [c_void_p]),
 }
 
-ABI_VERSION = 2  # include/fava_b200.h: FAVA_ABI_VERSION
+ABI_VERSION = 3  # include/fava_b200.h: FAVA_ABI_VERSION
 _lib = None
 
 

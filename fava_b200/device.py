@@ -512,11 +512,11 @@ def a2a_pack(src: int, peer_table: torch.Tensor, ky_of_dest: torch.Tensor, rank:
                                      nz_local, n, nyl, _stream(peer_table)), "fava_a2a_pack")
 
 
-def spectrum_bin(fx: int, fy: int, fz: int, n: int, ny_local: int, ky_of_local, local_of_ky, sums: torch.Tensor) -> None:
+def spectrum_bin(fx: int, fy: int, fz: int, n: int, ny_local: int, ky_of_local, sums: torch.Tensor) -> None:
     ctx = get_context(sums.device)
     norm = 1.0 / (float(n) ** 3)
     _lib.check(ctx.lib.fava_spectrum_bin(ctx.handle, C.c_void_p(fx), C.c_void_p(fy), C.c_void_p(fz), n, ny_local,
-                                         _ptr(ky_of_local), _ptr(local_of_ky), norm, _ptr(sums), _stream(sums)),
+                                         _ptr(ky_of_local), norm, _ptr(sums), _stream(sums)),
                "fava_spectrum_bin")
 
 

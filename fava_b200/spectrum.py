@@ -6,8 +6,9 @@ Rank r holds z-planes [r*nzl, (r+1)*nzl) of rho, ux, uy, uz.
   destination owns and stores them straight into that rank's receive buffer over NVLink peer mappings) ->
   stage 3 (z transform, pruned to the spectral sphere) ; then shell binning (K6) and one all-reduce of the
   [3][N/2-1] shell sums.  (Grid sizes that are not a power of two in [256, 2048] run the same schedule on cuFFT.)
-Spectral space is distributed over ky in +-ky symmetric sets, so the transposed operand
-u^(kz, +-ky, kx) the reference's `.T` projection needs (FlashUniform.py:281) is always rank-local.
+Spectral space is distributed over ky cyclically in |ky| (every rank bins the same share of the spectral sphere); the
+reference's `.T` projection (FlashUniform.py:281) is evaluated point by point without a transposed operand
+(csrc/spectrum.cu), so no rank needs another rank's rows.
 """
 
 from __future__ import annotations
@@ -64,11 +65,7 @@ class SlabPlan:
         own = ky_ownership(n, world)
         self.nyl = own.shape[1]
         self.ky_of_dest = torch.from_numpy(own).to(dev)
-        mine = own[rank]
-        inv = -np.ones(n, dtype=np.int32)
-        inv[mine[mine >= 0]] = np.flatnonzero(mine >= 0).astype(np.int32)
-        self.ky_of_local = torch.from_numpy(mine.copy()).to(dev)
-        self.local_of_ky = torch.from_numpy(inv).to(dev)
+        self.ky_of_local = torch.from_numpy(own[rank].copy()).to(dev)
         owner = -np.ones(n, dtype=np.int32)  # rank that owns global ky row k, and k's row inside that rank's set
         row = np.zeros(n, dtype=np.int32)
         for r in range(world):
@@ -174,7 +171,7 @@ def spectrum_from_transformed_slabs(n: int, dev, epilogue=None) -> dict[str, np.
     sums = torch.zeros((3, n // 2 - 1), dtype=torch.float64, device=dev)
     for c in range(3):
         device.ke_transform_z(w[c], n, n, None, dev)
-    device.spectrum_bin(w[0], w[1], w[2], n, n, None, None, sums)
+    device.spectrum_bin(w[0], w[1], w[2], n, n, None, sums)
     if epilogue is not None:
         epilogue()
     return device.spectrum_finalize(sums, n)
@@ -245,7 +242,7 @@ def slab_ke_spectrum(rho, ux, uy, uz, n: int, overlap=None, epilogue=None, xy_do
         cur.wait_event(p.ev_done[c])
         device.ke_transform_z(p.recv[c], n, p.nyl, p.ky_of_local, dev)
     p.ev_mark["fft_z"].record(cur)
-    device.spectrum_bin(p.recv[0], p.recv[1], p.recv[2], n, p.nyl, p.ky_of_local, p.local_of_ky, p.sums)
+    device.spectrum_bin(p.recv[0], p.recv[1], p.recv[2], n, p.nyl, p.ky_of_local, p.sums)
     # shell sums and counts add across ranks; this collective also fences the receive buffers against
     # the next call's remote stores (a rank's next exchange is stream-ordered after it)
     p.ev_mark["bin"].record(cur)

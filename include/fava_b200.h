@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define FAVA_ABI_VERSION 2
+#define FAVA_ABI_VERSION 3
 
 /* status codes */
 #define FAVA_OK 0
@@ -244,12 +244,14 @@ int fava_fft_y_scatter(fava_ctx* ctx, double* d_data, int64_t n, int64_t nz_chun
 int fava_a2a_pack(fava_ctx* ctx, const double* d_in, double* const* d_peer_recv, const int32_t* d_ky_of_dest,
                   int my_rank, int nranks, int64_t nz_local, int64_t n, int64_t nyl, void* stream);
 /* Shell binning of one spectral sub-volume complex [n (kz)][ny_local][pitch] x 3 components of an n^3
- * transform scaled by `norm` (1/n^3, norm="forward"), row pitch fava_spectral_pitch(n).  Row jl holds global ky index d_ky_of_local[jl];
- * d_local_of_ky[n] is the inverse (-1 = not held); both NULL = this GPU holds every ky in order.
+ * transform scaled by `norm` (1/n^3, norm="forward"), row pitch fava_spectral_pitch(n).  Row jl holds global ky index
+ * d_ky_of_local[jl] (NULL = this GPU holds every ky in order; -1 = padding row).  One streaming pass over the elements
+ * inside the spectral sphere: the reference's `.T` projection (FlashUniform.py:281) is evaluated at every point from
+ * the values stored AT that point, | kz u^_x + ky u^_y + kx u^_z |^2 / |k|^2 - the shell sums are those of the
+ * reference's transposed form (csrc/spectrum.cu), so the ky rows may be distributed over the ranks in any way.
  * d_sums: [3][n/2-1] = weighted sums of total, longitudinal, and the point counts (FlashUniform.py:273-293). */
 int fava_spectrum_bin(fava_ctx* ctx, const double* d_fx, const double* d_fy, const double* d_fz, int64_t n,
-                      int64_t ny_local, const int32_t* d_ky_of_local, const int32_t* d_local_of_ky, double norm,
-                      double* d_sums, void* stream);
+                      int64_t ny_local, const int32_t* d_ky_of_local, double norm, double* d_sums, void* stream);
 /* Shell sums -> spectra (host outputs, nbins = n/2-1 each): mean x 4 pi k^2 (FlashUniform.py:286-302). */
 int fava_spectrum_finalize(fava_ctx* ctx, const double* d_sums, int64_t n, double* h_k, double* h_total,
                            double* h_long, double* h_trans, void* stream);

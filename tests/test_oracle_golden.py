@@ -119,3 +119,27 @@ def test_slice_integral_and_average_bit_exact():
     span, alp = orc.slice_integral(geom, data["dens"], 0)
     assert np.array_equal(span, g["span"]) and np.array_equal(alp, g["integral_dens"])
     assert np.array_equal(orc.slice_average(geom, data["velx"], 0)[1], g["average_velx"])
+
+
+def test_transposed_projection_equals_the_pointwise_form_shell_by_shell():
+    """The identity the binning kernel rests on (csrc/spectrum.cu): the reference sums |sum_n k_n u^_n(rev k)|^2 / |k|^2 over a
+    shell (`ffts[n].T`, FlashUniform.py:281); rev is a bijection of the cube that keeps |k|, so the shell sums equal those of
+    |k_z u^_x(k) + k_y u^_y(k) + k_x u^_z(k)|^2 / |k|^2 - every term from the values stored at k alone."""
+    rng = np.random.default_rng(11)
+    n = 16
+    dens = 1.0 + 0.5 * rng.random((n, n, n))
+    vel = [rng.standard_normal((n, n, n)) for _ in range(3)]
+    kk = np.linspace(-n // 2, n // 2 - 1, n)
+    k = np.array(np.meshgrid(kk, kk, kk, indexing="ij"))
+    kabs = np.sqrt((k**2).sum(axis=0))
+    ffts = np.array([np.fft.fftshift(np.fft.fftn(np.sqrt(dens) * v, norm="forward")) for v in vel])
+    ref = np.zeros((n, n, n), dtype=np.complex128)
+    for i in range(3):
+        ref += k[i] * ffts[i].T  # the reference's line
+    ref = np.abs(ref / np.maximum(kabs, 1e-99)) ** 2
+    mine = np.abs((k[2] * ffts[0] + k[1] * ffts[1] + k[0] * ffts[2]) / np.maximum(kabs, 1e-99)) ** 2
+    assert np.allclose(np.sort(ref.ravel()), np.sort(mine.ravel()), rtol=1e-12, atol=1e-300)  # the same multiset of terms
+    shell = np.floor(kabs + 0.5).astype(int).ravel()
+    a = np.bincount(shell, weights=ref.ravel())
+    b = np.bincount(shell, weights=mine.ravel())
+    assert np.max(np.abs(a - b)) <= 1e-14 * np.max(np.abs(a))
