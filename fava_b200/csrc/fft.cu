@@ -260,7 +260,8 @@ __global__ void __launch_bounds__(XRowLayout<T, LOGN>::THREADS, CTAS)
         __syncthreads();  // landing row and sqrt(rho) consumed: refill them while this row is transformed
         if (threadIdx.x == 0 && row + gridDim.x < nrows) issue(row + gridDim.x);
         double2 e[8], o[8], mid;
-        fft_regs_half<LOGH>(v, u, at, xb, t1, t2, line_sync);
+        // second exchange through warp shuffles (the M2 partner threads are adjacent lanes): 10.67 -> 10.09 ms at 1024^3
+        fft_regs_half<LOGH, LineAddr, LineSync<M1>, 1>(v, u, at, xb, t1, t2, line_sync);
         split_two_for_one<LOGH>(v, u, at, xb, e, o, line_sync, &mid);
         double2* orow = out + row * out_pitch;
 #pragma unroll
@@ -386,7 +387,9 @@ __global__ void __launch_bounds__(512, 1)
             next_slot[(it + 1) & 1] = tn;
             if (tn < ntiles) issue(tn);
         }
-        fft_regs_half<LOGN>(v, u, at, xb, t1, t2);
+        // second exchange through warp shuffles in the y pass (M2 C = 32 lanes hold one exchange group; measured
+        // 2.95 -> 2.88 ms at 1024^3, profiles/r02_fft_lab5_*.txt); the z pass measured no gain and keeps shared memory
+        fft_regs_half<LOGN, ColAddr<C>, CtaSync, LINE_DIM == 1 ? C : 0>(v, u, at, xb, t1, t2);
         if (SCATTER) {
             const int64_t zoff = b * (int64_t)sc.nyl * rstride + kx0 + c;  // plane b of the destination's [z][row][kx]
 #pragma unroll

@@ -240,6 +240,41 @@ struct LineSync {
     }
 };
 
+// Exchange 2 without shared memory.  The M2 threads (q, j2 = 0..M2-1) that must swap points before pass 3 always sit in
+// ONE warp, `stride` lanes apart (column kernels: stride = C, a warp is exactly one q; x-row kernel: stride = 1): thread
+// j2 holds q2 = 0..15 and needs q2 = h G + i (h = its own index, i < G) from every j2.  That is the transpose of an
+// M2 x M2 matrix of G-point blocks, one row per thread: log2(M2) rounds of __shfl_xor, each swapping the blocks whose
+// index bit differs from the thread's, then a register renaming (block j, point i) -> i M2 + j.  No barrier, no bank.
+template <int M2>
+__device__ __forceinline__ void exchange2_shuffle(double2 (&v)[16], int j2, int stride) {
+    constexpr int G = 16 / M2;
+#pragma unroll
+    for (int bit = 1; bit < M2; bit <<= 1) {
+        const bool up = (j2 & bit) != 0;
+#pragma unroll
+        for (int h0 = 0; h0 < M2; ++h0) {
+            if (h0 & bit) continue;
+            const int h1 = h0 | bit;
+#pragma unroll
+            for (int i = 0; i < G; ++i) {
+                const double2 send = up ? v[h0 * G + i] : v[h1 * G + i];
+                double2 recv;
+                recv.x = __shfl_xor_sync(0xffffffffu, send.x, stride * bit);
+                recv.y = __shfl_xor_sync(0xffffffffu, send.y, stride * bit);
+                if (up) v[h0 * G + i] = recv;
+                else v[h1 * G + i] = recv;
+            }
+        }
+    }
+    double2 w[16];
+#pragma unroll
+    for (int j = 0; j < M2; ++j)
+#pragma unroll
+        for (int i = 0; i < G; ++i) w[i * M2 + j] = v[j * G + i];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = w[r];
+}
+
 // Everything between "v holds the inputs of pass 1" and "v holds the outputs": two exchanges through `xb`
 // (complex words).  u = thread's index within the line.  All threads that `sync` joins must call it.
 template <int LOGN, class Addr, class Sync = CtaSync>
@@ -269,7 +304,7 @@ __device__ __forceinline__ void fft_regs_full(double2 (&v)[16], int u, const Add
 
 // Same with an exchange buffer of 8-byte words (half the size): real and imaginary parts go through it one after the
 // other (twice the barriers, same traffic).
-template <int LOGN, class Addr, class Sync = CtaSync>
+template <int LOGN, class Addr, class Sync = CtaSync, int SHFL_STRIDE = 0>
 __device__ __forceinline__ void fft_regs_half(double2 (&v)[16], int u, const Addr& at, double* __restrict__ xb,
                                               const double2* __restrict__ t1, const double2* __restrict__ t2,
                                               const Sync& sync = Sync()) {
@@ -291,17 +326,22 @@ __device__ __forceinline__ void fft_regs_half(double2 (&v)[16], int u, const Add
     dft16(v);
     if constexpr (P::M2 > 1) {
         twiddle2<LOGN>(v, u, t2);
+        if constexpr (SHFL_STRIDE > 0) {
+            static_assert(P::M2 * SHFL_STRIDE <= 32, "the exchange group must sit inside one warp");
+            exchange2_shuffle<P::M2>(v, u % P::M2, SHFL_STRIDE);
+        } else {
 #pragma unroll
-        for (int q = 0; q < 16; ++q) xb[at(O::x2_write(u, q))] = v[q].x;  // own slots of the last read
-        sync();
+            for (int q = 0; q < 16; ++q) xb[at(O::x2_write(u, q))] = v[q].x;  // own slots of the last read
+            sync();
 #pragma unroll
-        for (int r = 0; r < 16; ++r) v[r].x = xb[at(O::x2_read(u, r))];  // v[].y still holds pass-2 ownership
-        sync();
+            for (int r = 0; r < 16; ++r) v[r].x = xb[at(O::x2_read(u, r))];  // v[].y still holds pass-2 ownership
+            sync();
 #pragma unroll
-        for (int q = 0; q < 16; ++q) xb[at(O::x2_write(u, q))] = v[q].y;
-        sync();
+            for (int q = 0; q < 16; ++q) xb[at(O::x2_write(u, q))] = v[q].y;
+            sync();
 #pragma unroll
-        for (int r = 0; r < 16; ++r) v[r].y = xb[at(O::x2_read(u, r))];
+            for (int r = 0; r < 16; ++r) v[r].y = xb[at(O::x2_read(u, r))];
+        }
         dft_groups<P::M2>(v);
     }
 }

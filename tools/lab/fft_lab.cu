@@ -168,7 +168,11 @@ __global__ void __launch_bounds__(RegPlan<LOGN>::M1 * C, 1)
         __syncthreads();  // landing buffer consumed (and the previous tile's exchange reads are complete)
         const int64_t tn = next_tile(t + gridDim.x);
         if (threadIdx.x == 0 && tn < ntiles) issue(tn);
+#ifdef FAVA_LAB_SHFL
+        if (MODE == 0) fft_regs_half<LOGN, ColAddr<C>, CtaSync, C>(v, u, ColAddr<C>{c}, xb, t1, t2);
+#else
         if (MODE == 0) fft_regs_half<LOGN>(v, u, ColAddr<C>{c}, xb, t1, t2);
+#endif
         double2* base = data + b * bstride + kx0 + c;
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
@@ -343,7 +347,11 @@ __global__ void __launch_bounds__(XRowLayout<T, LOGN>::THREADS, CTAS)
         double2* orow = out + row * out_pitch;
         if (MODE == 0) {
             double2 e[8], o[8], mid;
+#ifdef FAVA_LAB_SHFL
+            fft_regs_half<LOGH, LineAddr, LineSync<M1>, 1>(v, u, at, xb, t1, t2, line_sync);
+#else
             fft_regs_half<LOGH>(v, u, at, xb, t1, t2, line_sync);
+#endif
             split_two_for_one<LOGH>(v, u, at, xb, e, o, line_sync, &mid);
 #pragma unroll
             for (int m = 0; m < 8; ++m) {
