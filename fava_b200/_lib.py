@@ -78,6 +78,11 @@ SIGNATURES: dict[str, tuple] = {
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_i64, c_i64, c_int,
          C.POINTER(LeafDesc), c_i64, c_i64, c_void_p, c_void_p, c_void_p],
     ),
+    "fava_plane_moments_blocks_uid": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_i64, c_i64, c_int,
+         C.POINTER(LeafDesc), c_i64, C.c_uint64, c_i64, c_void_p, c_void_p, c_void_p],
+    ),
     "fava_moments_repivot": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p]),
     "fava_moments_finalize": (
         c_int,
@@ -87,6 +92,11 @@ SIGNATURES: dict[str, tuple] = {
     "fava_plane_sum_blocks": (
         c_int,
         [c_void_p, c_void_p, c_int, c_i64, c_i64, c_i64, c_int, C.POINTER(LeafDesc), c_i64, c_i64, c_void_p, c_void_p],
+    ),
+    "fava_plane_sum_blocks_uid": (
+        c_int,
+        [c_void_p, c_void_p, c_int, c_i64, c_i64, c_i64, c_int, C.POINTER(LeafDesc), c_i64, C.c_uint64, c_i64, c_void_p,
+         c_void_p],
     ),
     "fava_prolong": (
         c_int,
@@ -156,7 +166,7 @@ SIGNATURES: dict[str, tuple] = {
     "fava_ipc_close": (c_int, [c_void_p]),
 }
 
-ABI_VERSION = 3  # include/fava_b200.h: FAVA_ABI_VERSION
+ABI_VERSION = 4  # include/fava_b200.h: FAVA_ABI_VERSION
 _lib = None
 
 

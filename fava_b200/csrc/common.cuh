@@ -69,6 +69,8 @@ struct fava_ctx {
     std::map<std::tuple<int, int64_t, int64_t, int64_t>, size_t> plan_work;  // work-area bytes per plan
     // host copies of the leaf tables whose device CSR tables are cached in WS_ITEMS0 + axis (block_moments.cu)
     std::string item_cache_key[3];
+    uint64_t item_cache_uid[3] = {0, 0, 0};  // caller's table id of the cached tables (0 = none given)
+    int64_t item_cache_nunits[3] = {0, 0, 0}, item_cache_nent[3] = {0, 0, 0};  // sizes of the cached tables
     std::string prolong_cache_key;  // same for the lattice table of fava_prolong (WS_TABLE)
     std::map<int64_t, void*> twiddles;  // twiddle tables of the hand-written FFT, per N (fft.cu)
     std::map<std::string, CUtensorMap> tensor_maps;  // TMA descriptors, keyed by (base, dtype, dims, strides, box)

@@ -8,6 +8,7 @@ file layout ([z][y][x], x fastest) and enqueue on torch's current stream.
 from __future__ import annotations
 
 import ctypes as C
+import itertools
 
 import numpy as np
 import torch
@@ -230,10 +231,16 @@ PROLONG_DTYPE = np.dtype([("block", "<i8"), ("off", "<i4", (3,)), ("scale", "<i4
 
 
 class HostTable:
-    """A host array of C structs (numpy structured array) plus its ctypes pointer."""
+    """A host array of C structs (numpy structured array) plus its ctypes pointer.  Immutable once built (the array
+    is made read-only), so `uid` identifies its contents: the library reuses the device tables it derived from a
+    table with the same uid without comparing the bytes again (fava_plane_moments_blocks_uid)."""
+
+    _uids = itertools.count(1)
 
     def __init__(self, arr: np.ndarray, ctype):
-        self.arr = np.ascontiguousarray(arr)
+        self.arr = np.array(arr, copy=True, order="C")  # private copy: nobody else can write to it
+        self.arr.flags.writeable = False
+        self.uid = next(HostTable._uids)
         self.n = int(arr.shape[0])
         self.ptr = C.cast(C.c_void_p(self.arr.ctypes.data if self.n else 0), C.POINTER(ctype))
 
@@ -255,10 +262,10 @@ def plane_moments_blocks(rho, ux, uy, uz, axis: int, table: HostTable, nbins: in
     mom = torch.empty((FAVA_NMOM, nbins), dtype=torch.float64, device=rho.device)
     piv = torch.empty((3, nbins), dtype=torch.float64, device=rho.device)
     _lib.check(
-        ctx.lib.fava_plane_moments_blocks(ctx.handle, _ptr(rho), _ptr(ux), _ptr(uy), _ptr(uz), _dtype_code(rho), nzb,
-                                          nyb, nxb, int(axis), table.ptr, table.n, int(nbins), _ptr(mom), _ptr(piv),
-                                          _stream(rho)),
-        "fava_plane_moments_blocks",
+        ctx.lib.fava_plane_moments_blocks_uid(ctx.handle, _ptr(rho), _ptr(ux), _ptr(uy), _ptr(uz), _dtype_code(rho),
+                                              nzb, nyb, nxb, int(axis), table.ptr, table.n, table.uid, int(nbins),
+                                              _ptr(mom), _ptr(piv), _stream(rho)),
+        "fava_plane_moments_blocks_uid",
     )
     return mom, piv
 
@@ -282,9 +289,10 @@ def plane_sum_blocks(blocks: torch.Tensor, axis: int, table: HostTable, nbins: i
         raise ValueError(f"Do not recognize AXIS enumeration {axis}")
     ctx = get_context(blocks.device)
     out = torch.empty(nbins, dtype=torch.float64, device=blocks.device)
-    _lib.check(ctx.lib.fava_plane_sum_blocks(ctx.handle, _ptr(blocks), _dtype_code(blocks), nzb, nyb, nxb, int(axis),
-                                             table.ptr, table.n, int(nbins), _ptr(out), _stream(blocks)),
-               "fava_plane_sum_blocks")
+    _lib.check(ctx.lib.fava_plane_sum_blocks_uid(ctx.handle, _ptr(blocks), _dtype_code(blocks), nzb, nyb, nxb, int(axis),
+                                                 table.ptr, table.n, table.uid, int(nbins), _ptr(out),
+                                                 _stream(blocks)),
+               "fava_plane_sum_blocks_uid")
     return out
 
 

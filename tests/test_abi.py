@@ -32,7 +32,7 @@ def test_ctypes_table_matches_header(built_lib):
 
     assert sorted(_lib.SIGNATURES) == _declared_symbols()
     lib = _lib.load()
-    assert lib.fava_abi_version() == _lib.ABI_VERSION == 3
+    assert lib.fava_abi_version() == _lib.ABI_VERSION == 4
     assert lib.fava_launch_count() == 0
 
 

@@ -225,3 +225,46 @@ def test_three_axis_pass_equals_per_axis_passes(cuda_device, shape, dtype):
             maxnorm_close(got[k].cpu().numpy(), want[k].cpu().numpy(), rtol=1e-13, what=f"xyz {k} axis {axis} {shape}")
     again = device.plane_moments_xyz(*f)
     assert all(torch.equal(a[0], b[0]) for a, b in zip(res, again))
+
+
+@pytest.mark.parametrize("block,dtype", [((8, 8, 8), torch.float32), ((8, 8, 8), torch.float64), ((16, 8, 8), torch.float32),
+                                         ((4, 4, 4), torch.float32)])
+def test_small_blocks_streamed_through_the_leaf_ring(cuda_device, block, dtype):
+    """Blocks of <= 16 KB take the persistent kernel that streams leaves through shared-memory rings
+    (k_block_moments_ring): enough leaves that every group recycles its slots several times, leaves in a shuffled
+    order, all three axes, against the dense kernels on the assembled array; bitwise repeatable."""
+    from fava_b200 import device
+
+    nzb, nyb, nxb = block
+    per = (8, 16, 32)  # blocks along z, y, x
+    nz, ny, nx = per[0] * nzb, per[1] * nyb, per[2] * nxb
+    nblk = per[0] * per[1] * per[2]
+    g = torch.Generator(device=cuda_device)
+    g.manual_seed(17 + nzb)
+    dense = [(torch.rand((nz, ny, nx), generator=g, device=cuda_device, dtype=torch.float64) + (0.5 if i == 0 else 7.0 * i)).to(dtype)
+             for i in range(4)]
+    perm = np.random.default_rng(5).permutation(nblk)  # file order of the blocks
+
+    def to_blocks(a):
+        b = a.view(per[0], nzb, per[1], nyb, per[2], nxb).permute(0, 2, 4, 1, 3, 5).reshape(nblk, nzb, nyb, nxb)
+        out = torch.empty_like(b)
+        out[torch.from_numpy(perm).to(cuda_device)] = b  # lattice block i is stored as block perm[i]
+        return out.contiguous()
+
+    blocks = [to_blocks(a) for a in dense]
+    lattice = np.arange(nblk)
+    bz, by, bx = lattice // (per[1] * per[2]), (lattice // per[2]) % per[1], lattice % per[2]
+    cv = 1.0 / (nz * ny * nx)
+    for axis in (0, 1, 2):
+        nbins = (nx, ny, nz)[axis]
+        ilo = ((bx * nxb), (by * nyb), (bz * nzb))[axis]
+        order = np.random.default_rng(axis).permutation(nblk)  # leaf order of the table
+        table = device.leaf_table(perm[order], ilo[order], np.ones(nblk, dtype=np.int64), np.full(nblk, cv))
+        mom, piv = device.plane_moments_blocks(*blocks, axis, table, nbins)
+        lv = 1.0 / nbins
+        got = device.moments_finalize(mom, piv, 1.0, lv)
+        want = device.plane_profiles(*dense, axis, cv, lv)
+        for k in want:
+            maxnorm_close(got[k].cpu().numpy(), want[k].cpu().numpy(), rtol=1e-12, what=f"ring {k} axis {axis} {block}")
+        again, _ = device.plane_moments_blocks(*blocks, axis, table, nbins)
+        assert torch.equal(mom, again)

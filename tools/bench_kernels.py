@@ -43,6 +43,7 @@ def main():
     g = torch.Generator(device=dev)
     g.manual_seed(3)
     # ---- K1b on a single-level multi-block file layout: 512^3 cells in 16^3 blocks, f32 (config 5 per-GPU share)
+    blocks_only = "blocks" in sys.argv[1:]  # the block-list kernels alone (used under ncu)
     for nb, n in ((16, 512), (8, 512)):
         nblk = (n // nb) ** 3
         f = [torch.rand((nblk, nb, nb, nb), generator=g, device=dev, dtype=torch.float32) + (1.0 if i == 0 else -0.5) for i in range(4)]
@@ -55,6 +56,9 @@ def main():
             record(f"block_moments_{nb}cubed_f32_axis{axis}", ms, 16.0 * n**3,
                    f"fava_plane_moments_blocks incl. host CSR build + table upload; {nblk} leaves of {nb}^3, 16 B/cell")
         del f
+    if blocks_only:
+        print(json.dumps(out))
+        return
     # ---- K1b + K3 on the C2 mesh: 8^3 blocks, 4 levels -> 256^3
     mesh = synth.octree_mesh((4, 4, 4), (8, 8, 8), 4, seed=11, p_refine=0.5)
     leaves = np.flatnonzero(mesh.node_type == 1)

@@ -3,7 +3,6 @@
 (algorithmic bytes = s per cell, the field read once) and the structure-function gather / moment kernels
 (csrc/structure.cu; random 4-byte gathers, reported as pairs/s).  CUDA-event times; prints one JSON line."""
 import json
-import os
 import sys
 from pathlib import Path
 
@@ -37,9 +36,7 @@ def main():
         ar = torch.arange(n, device=dev, dtype=torch.float64)
         sheet = (ar[None, None, :] - 0.5 * n - 0.25 - 20.0 * torch.sin(2 * np.pi * ar / n)[None, :, None]
                  * torch.cos(4 * np.pi * ar / n)[:, None, None]).to(dt)  # a wrinkled surface: the realistic case
-        for shape in (os.environ.get("FAVA_BENCH_CTA_SHAPES") or "default").split(","):
-            if shape != "default":
-                os.environ["FAVA_FRACTAL_CTA"] = shape
+        for shape in ("default",):
             for contour, tag in ((0.5, "noise"), (2.0, "empty"), (0.0, "sheet")):
                 src = sheet if tag == "sheet" else f
 
@@ -55,7 +52,6 @@ def main():
                     "ms": ms, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / ms / 1e6,
                     "frac_of_hbm_peak": nbytes / ms / 1e6 / peak, "gcells_per_s": n**3 / ms / 1e6,
                     "note": "counts.zero_ + fava_fractal_tiles" + ("" if tiles_only else " + fava_fractal_coarse")}
-        os.environ.pop("FAVA_FRACTAL_CTA", None)
         del f, sheet
     if quick:
         print(json.dumps(out))
