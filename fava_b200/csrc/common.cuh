@@ -86,8 +86,9 @@ int ctx_workspace(fava_ctx* ctx, int slot, size_t bytes, void** out);
 
 // Cached tiled TMA descriptor (cuTensorMapEncodeTiled through the runtime's driver entry point; no swizzle, no
 // interleave, 128-byte L2 promotion).  dims / box in elements, strides in bytes (rank - 1 of them), innermost first.
+// nan_fill: elements of a box that lie outside the tensor read as NaN instead of 0.
 int ctx_tensor_map(fava_ctx* ctx, const void* base, CUtensorMapDataType dtype, int rank, const uint64_t* dims,
-                   const uint64_t* strides_bytes, const uint32_t* box, CUtensorMap* out);
+                   const uint64_t* strides_bytes, const uint32_t* box, CUtensorMap* out, bool nan_fill = false);
 
 // hand-written FFT path for this grid size?  (power of two in [256, 2048]; other even N use cuFFT)
 bool fft_native_supported(int64_t n);

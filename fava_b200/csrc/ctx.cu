@@ -47,8 +47,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 int ctx_tensor_map(fava_ctx* ctx, const void* base, CUtensorMapDataType dtype, int rank, const uint64_t* dims,
-                   const uint64_t* strides_bytes, const uint32_t* box, CUtensorMap* out) {
+                   const uint64_t* strides_bytes, const uint32_t* box, CUtensorMap* out, bool nan_fill) {
     std::string key((const char*)&base, sizeof(base));
+    key.push_back(nan_fill ? 'n' : 'z');
     key.append((const char*)&dtype, sizeof(dtype));
     key.append((const char*)dims, sizeof(uint64_t) * rank);
     key.append((const char*)strides_bytes, sizeof(uint64_t) * (rank - 1));
@@ -73,7 +74,8 @@ int ctx_tensor_map(fava_ctx* ctx, const void* base, CUtensorMapDataType dtype, i
     for (int i = 0; i + 1 < rank; ++i) sb[i] = strides_bytes[i];
     CUtensorMap m;
     const CUresult r = enc(&m, dtype, (cuuint32_t)rank, const_cast<void*>(base), d, sb, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           nan_fill ? CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA : CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
         return set_error(FAVA_ECUDA, "cuTensorMapEncodeTiled(rank %d, inner %llu, box %u) failed: CUresult %d", rank,
                          (unsigned long long)dims[0], box[0], (int)r);
