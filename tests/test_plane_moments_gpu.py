@@ -268,3 +268,28 @@ def test_small_blocks_streamed_through_the_leaf_ring(cuda_device, block, dtype):
             maxnorm_close(got[k].cpu().numpy(), want[k].cpu().numpy(), rtol=1e-12, what=f"ring {k} axis {axis} {block}")
         again, _ = device.plane_moments_blocks(*blocks, axis, table, nbins)
         assert torch.equal(mom, again)
+
+
+def test_leaf_table_uid_keys_the_cached_device_tables(cuda_device):
+    """Two immutable tables of the same length but different contents (weights, bins) must not share cached device
+    tables: the uid a HostTable carries is what the library's cache is keyed on (fava_plane_moments_blocks_uid)."""
+    from fava_b200 import device
+
+    nblk, nb, nbins = 64, 8, 64
+    g = torch.Generator(device=cuda_device)
+    g.manual_seed(3)
+    f = [torch.rand((nblk, nb, nb, nb), generator=g, device=cuda_device, dtype=torch.float32) + 0.5 for _ in range(4)]
+    blocks = np.arange(nblk)
+    ilo = (blocks % 8) * nb
+    ta = device.leaf_table(blocks, ilo, np.ones(nblk, dtype=np.int64), np.full(nblk, 1.0))
+    tb = device.leaf_table(blocks, ilo[::-1].copy(), np.ones(nblk, dtype=np.int64), np.full(nblk, 2.0))
+    assert ta.uid != tb.uid and not ta.arr.flags.writeable
+    with pytest.raises(ValueError):
+        ta.arr["vol_frac"][0] = 3.0
+    ma, _ = device.plane_moments_blocks(*f, 0, ta, nbins)
+    mb, _ = device.plane_moments_blocks(*f, 0, tb, nbins)
+    ma2, _ = device.plane_moments_blocks(*f, 0, ta, nbins)
+    assert torch.equal(ma, ma2)
+    # total density moment: table b weights every leaf twice
+    assert abs(float(mb[0].sum()) / float(ma[0].sum()) - 2.0) < 1e-12
+    assert not torch.equal(ma[0], 0.5 * mb[0])  # and maps the leaves to other bins
