@@ -641,6 +641,42 @@ def run_extras(rank, world, dev, peak) -> dict:
                                   "achieved_gbs": nbytes / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / peak,
                                   "note": "134 MB written: the output fits the 126 MB L2 only partly; see prolong_512 for a size that does not"}
         del blk, dst
+        # ---- block-list moments (AMR / multi-block files): 512^3 cells f32 in 8^3 and 16^3 blocks, 16 B/cell ------
+        from fava_b200 import uniform_analysis as ua
+
+        n = 512
+        bm = {"workload": "reynolds_stress moments of a block file: 512^3 cells f32 as single-level 8^3 / 16^3 blocks, axis x "
+                          "(fava_plane_moments_blocks_uid; tables cached), 16 B/cell"}
+        for nb in (8, 16):
+            nblk, per = (n // nb) ** 3, n // nb
+            f = [torch.rand((nblk, nb, nb, nb), generator=g, device=dev, dtype=torch.float32) + (1.0 if i == 0 else -0.5)
+                 for i in range(4)]
+            b = np.arange(nblk)
+            table = device.leaf_table(b, (b % per) * nb, np.ones(nblk, dtype=np.int64), np.full(nblk, 1.0 / n**3))
+            ms = _timeit(lambda: device.plane_moments_blocks(*f, 0, table, n))
+            bm[f"blocks{nb}_ms"] = ms
+            bm[f"blocks{nb}_frac_of_hbm_peak"] = 16.0 * n**3 / (ms * 1e-3) / 1e9 / peak
+            del f
+        out["block_moments_512"] = bm
+        # ---- box counting (fractal_dimension): 1024^3 f32, a wrinkled iso-surface, s B/cell -------------------------
+        n = 1024
+        ar = torch.arange(n, device=dev, dtype=torch.float64)
+        sheet = (ar[None, None, :] - 0.5 * n - 0.25 - 20.0 * torch.sin(2 * np.pi * ar / n)[None, :, None]
+                 * torch.cos(4 * np.pi * ar / n)[:, None, None]).to(torch.float32)
+        counts = torch.zeros(32, dtype=torch.int64, device=dev)
+        coarse = torch.zeros([n // 32] * 3, dtype=torch.uint8, device=dev)
+
+        def count_boxes():
+            counts.zero_()
+            device.fractal_tiles(sheet, 0.0, n, 0, 0, n, counts, coarse)
+            device.fractal_coarse(coarse, (n, n, n), ua.box_levels((n, n, n)), counts)
+
+        ms = _timeit(count_boxes)
+        out["box_counting_1024"] = {"workload": "fractal_dimension box counts of a wrinkled sheet, 1024^3 f32 (fava_fractal_tiles + "
+                                                "fava_fractal_coarse), 4 B/cell", "ms": ms,
+                                    "frac_of_hbm_peak": 4.0 * n**3 / (ms * 1e-3) / 1e9 / peak,
+                                    "boxes_per_level": [int(v) for v in counts[: ua.box_levels((n, n, n))].tolist()]}
+        del sheet, counts, coarse
     # ---- prolongation sharded over ranks: 16^3 blocks, 4 levels -> 512^3, every rank fills its z-slab --------------------
     mesh = synth.octree_mesh((4, 4, 4), (16, 16, 16), 4, seed=11, p_refine=0.5)
     leaves = np.flatnonzero(mesh.node_type == 1)
