@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -85,7 +86,7 @@ template <typename T, int AXIS, int BT>
 __global__ void __launch_bounds__(BT, 1024 / BT)
     k_block_moments_pow2(const T* __restrict__ rho, const T* __restrict__ ux, const T* __restrict__ uy,
                          const T* __restrict__ uz, const fava_leaf_desc* __restrict__ leaves,
-                         const double* __restrict__ piv, int64_t nbins, int lx, int ly, int lz,
+                         const double* __restrict__ piv, int64_t nbins, int lx, int ly, int lz, int vec,
                          double* __restrict__ partial) {
     const int t = threadIdx.x;
     const fava_leaf_desc leaf = leaves[blockIdx.x];
@@ -113,6 +114,27 @@ __global__ void __launch_bounds__(BT, 1024 / BT)
     const T* py = uy + base + e0;
     const T* pz = uz + base + e0;
     int j = 0;
+    if (AXIS == 2 && vec) {
+        // along z the G threads of a plane stride its contiguous cells: 16-byte words per thread make a half-warp's
+        // request one 256-byte run instead of 64 bytes per plane (16^3 blocks f32: 0.50 -> 0.39 ms, x / y take 0.41)
+        constexpr int V = 16 / sizeof(T);
+        typedef typename std::conditional<sizeof(T) == 4, float4, double2>::type Vec;
+        const int first = (plane << (lx + ly)) + V * (t - plane * G);
+        const int nv = nit / V;  // vector loads per field and thread
+#pragma unroll 1
+        for (int q = 0; q < nv; ++q) {
+            const int64_t o = base + first + q * (V * G);
+            const Vec a = __ldcs(reinterpret_cast<const Vec*>(rho + o)), b = __ldcs(reinterpret_cast<const Vec*>(ux + o));
+            const Vec cc = __ldcs(reinterpret_cast<const Vec*>(uy + o)), d = __ldcs(reinterpret_cast<const Vec*>(uz + o));
+            const T* ar = reinterpret_cast<const T*>(&a);
+            const T* br = reinterpret_cast<const T*>(&b);
+            const T* cr = reinterpret_cast<const T*>(&cc);
+            const T* dr = reinterpret_cast<const T*>(&d);
+#pragma unroll
+            for (int k = 0; k < V; ++k) acc.add((double)ar[k], (double)br[k], (double)cr[k], (double)dr[k], c0, c1, c2);
+        }
+        j = nit;
+    }
     for (; j + 4 <= nit; j += 4) {
         double vr[4], vx[4], vy[4], vz[4];
 #pragma unroll
@@ -610,8 +632,10 @@ static int run_blocks(fava_ctx* ctx, const T* rho, const T* ux, const T* uy, con
     FAVA_LAUNCHED();
     if (nleaf) {
         const unsigned grid = (unsigned)nleaf;
+        // z planes read as 16-byte words: aligned fields, and a plane's cells a multiple of what its threads take per load
+        const int vec2 = aligned16 && fits(kBT) && ((nxb * nyb) % ((16 / (int)sizeof(T)) * (kBT / nzb))) == 0;
 #define FAVA_LAUNCH_POW2(AX, BTV) \
-    k_block_moments_pow2<T, AX, BTV><<<grid, BTV, 0, st>>>(rho, ux, uy, uz, tb.leaves, piv, nbins, lx, ly, lz, partial)
+    k_block_moments_pow2<T, AX, BTV><<<grid, BTV, 0, st>>>(rho, ux, uy, uz, tb.leaves, piv, nbins, lx, ly, lz, vec2, partial)
         if (ring) {
             const int stages = (int)std::min<size_t>(8, (kRingSmem / groups - sums_bytes) / stage_bytes);
             const size_t dyn = (size_t)groups * (stages * stage_bytes + sums_bytes + sizeof(uint64_t) * stages);
