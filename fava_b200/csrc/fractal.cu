@@ -14,18 +14,20 @@
 // oracle, which divides, against this on adversarial inputs).
 //
 // One CTA owns a 32^3 tile and works in four phases on 32-bit row words (one bit per cell of an x row):
-//   A  every row of the tile and of its y/z halo (34 x 34 rows) is read ONCE, coalesced, and classified against the
-//      contour: words lt (val < c), gt (val > c) and, for the tile's own rows, eq (val == c).  f32 data is compared
-//      in f32 against the contour rounded up / down (val < c <=> val < ru(c), val > c <=> val > rd(c): exact);
+//   A  every row of the tile and of its y/z halo (34 x 34 rows) is read ONCE and classified against the contour:
+//      words lt (val < c), gt (val > c) and, for the tile's own rows, eq (val == c).  f32 data is compared in f32
+//      against the contour rounded up / down (val < c <=> val < ru(c), val > c <=> val > rd(c): exact).  Two front
+//      ends: k_fractal_tiles_tma (rows of a multiple of 16 bytes: planes by TMA into per-warp slots, a lane
+//      classifies a whole row out of shared memory) and k_fractal_tiles (any shape: coalesced loads + ballots);
 //   B  one thread per row combines the words of the six neighbour rows (x neighbours by shifts, the two x-halo
-//      cells of the row loaded by that thread) into CANDIDATES: low visited cells with a high neighbour, high cells
-//      with a low visited neighbour.  Every other cell is decided: flagged iff eq;
-//   C  candidate cells (the cells next to the surface) are evaluated exactly, one lane per cell, with the rule
-//      above on the seven fp64 values (L1/L2 hits: the tile was just read);
+//      cells of the row from phase A) into CANDIDATES: low visited cells with a high neighbour, high cells with a
+//      low visited neighbour.  Every other cell is decided: flagged iff eq;
+//   C  candidate cells (the cells next to the surface) are evaluated exactly with the rule above on the seven fp64
+//      values, dealt to the lanes cell by cell (row by row in tiles crowded with candidates), branch-free;
 //   D  the 32 x 32 flag words are folded level by level in shared memory (levels 0..5); the tile's occupancy goes
 //      to a coarse byte grid from which k_fractal_coarse counts the levels above.
-// HBM-bound: s bytes per cell read once (+ halo rows from L2); counts are integers (atomic adds are exact and
-// order-independent).
+// HBM-bound: s bytes per cell read once (+ halo planes / lines, 6 %); counts are integers (atomic adds are exact
+// and order-independent).
 #include <stdlib.h>
 #include <string.h>
 
