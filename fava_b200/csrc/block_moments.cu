@@ -727,7 +727,9 @@ static int run_block_sum(fava_ctx* ctx, const T* f, int64_t nzb, int64_t nyb, in
     const int nrb = (int)(axis == 0 ? nxb : (axis == 1 ? nyb : nzb));
     const int64_t nitems = nleaf * nrb;
     ItemTables tb;
-    int rc = build_item_tables(ctx, axis, h_leaves, nleaf, nrb, nxb * nyb * nzb, 0, nbins, 0, uid, st, &tb);
+    // same key and same tables as a per-leaf moments call on this mesh (pivot sources included, unused here)
+    const int64_t plane_stride = axis == 0 ? 1 : (axis == 1 ? nxb : nxb * nyb);
+    int rc = build_item_tables(ctx, axis, h_leaves, nleaf, nrb, nxb * nyb * nzb, plane_stride, nbins, 0, uid, st, &tb);
     if (rc) return rc;
     void* ws;
     rc = ctx_workspace(ctx, WS_PARTIALS, sizeof(double) * (size_t)std::max<int64_t>(nitems, 1), &ws);
