@@ -81,12 +81,13 @@ struct Acc13 {
 //   axis x: element e = t + BT r           -> x = t mod nxb                     (plane = t & (nxb-1))
 //   axis y: same walk                      -> y = (t >> lx) mod nyb
 //   axis z: plane = t / G, G = BT/nzb lanes share a plane and stride its contiguous cells.
-// BT = 256 threads per leaf, 64 for small blocks (<= 1024 cells: more leaves in flight per SM).  The BT/nrb partial sums of a plane are then added in a fixed (rotated, bank-conflict-free) order.
-template <typename T, int AXIS, int BT>
+// BT = 256 threads per leaf (leaves of at most 16 KB take k_block_moments_ring below instead).  The BT/nrb partial
+// sums of a plane are then added in a fixed (rotated, bank-conflict-free) order.  VEC: 16-byte loads along z.
+template <typename T, int AXIS, int BT, bool VEC>
 __global__ void __launch_bounds__(BT, 1024 / BT)
     k_block_moments_pow2(const T* __restrict__ rho, const T* __restrict__ ux, const T* __restrict__ uy,
                          const T* __restrict__ uz, const fava_leaf_desc* __restrict__ leaves,
-                         const double* __restrict__ piv, int64_t nbins, int lx, int ly, int lz, int vec,
+                         const double* __restrict__ piv, int64_t nbins, int lx, int ly, int lz,
                          double* __restrict__ partial) {
     const int t = threadIdx.x;
     const fava_leaf_desc leaf = leaves[blockIdx.x];
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(BT, 1024 / BT)
     const T* py = uy + base + e0;
     const T* pz = uz + base + e0;
     int j = 0;
-    if (AXIS == 2 && vec) {
+    if (AXIS == 2 && VEC) {
         // along z the G threads of a plane stride its contiguous cells: 16-byte words per thread make a half-warp's
         // request one 256-byte run instead of 64 bytes per plane (16^3 blocks f32: 0.50 -> 0.39 ms, x / y take 0.41)
         constexpr int V = 16 / sizeof(T);
@@ -633,9 +634,9 @@ static int run_blocks(fava_ctx* ctx, const T* rho, const T* ux, const T* uy, con
     if (nleaf) {
         const unsigned grid = (unsigned)nleaf;
         // z planes read as 16-byte words: aligned fields, and a plane's cells a multiple of what its threads take per load
-        const int vec2 = aligned16 && fits(kBT) && ((nxb * nyb) % ((16 / (int)sizeof(T)) * (kBT / nzb))) == 0;
-#define FAVA_LAUNCH_POW2(AX, BTV) \
-    k_block_moments_pow2<T, AX, BTV><<<grid, BTV, 0, st>>>(rho, ux, uy, uz, tb.leaves, piv, nbins, lx, ly, lz, vec2, partial)
+        const bool vec2 = aligned16 && fits(kBT) && ((nxb * nyb) % ((16 / (int)sizeof(T)) * (kBT / nzb))) == 0;
+#define FAVA_LAUNCH_POW2(AX, BTV, VECV) \
+    k_block_moments_pow2<T, AX, BTV, VECV><<<grid, BTV, 0, st>>>(rho, ux, uy, uz, tb.leaves, piv, nbins, lx, ly, lz, partial)
         if (ring) {
             const int stages = (int)std::min<size_t>(8, (kRingSmem / groups - sums_bytes) / stage_bytes);
             const size_t dyn = (size_t)groups * (stages * stage_bytes + sums_bytes + sizeof(uint64_t) * stages);
@@ -653,9 +654,10 @@ static int run_blocks(fava_ctx* ctx, const T* rho, const T* ux, const T* uy, con
             else FAVA_LAUNCH_RING(2);
 #undef FAVA_LAUNCH_RING
         } else if (fits(kBT)) {
-            if (axis == 0) FAVA_LAUNCH_POW2(0, kBT);
-            else if (axis == 1) FAVA_LAUNCH_POW2(1, kBT);
-            else FAVA_LAUNCH_POW2(2, kBT);
+            if (axis == 0) FAVA_LAUNCH_POW2(0, kBT, false);
+            else if (axis == 1) FAVA_LAUNCH_POW2(1, kBT, false);
+            else if (vec2) FAVA_LAUNCH_POW2(2, kBT, true);
+            else FAVA_LAUNCH_POW2(2, kBT, false);
 #undef FAVA_LAUNCH_POW2
         } else {
             k_block_moments_generic<T><<<(unsigned)cdiv(nitems, kBT / 32), kBT, 0, st>>>(
